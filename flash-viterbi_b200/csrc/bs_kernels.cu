@@ -1,0 +1,249 @@
+// bs_kernels.cu — FLASH-BS passes on the device.
+//
+// One CTA owns one trellis vector (a sequence's first pass or one task) for all of its steps, so
+// a pass needs no grid-wide synchronisation: per step the CTA's threads score every destination
+// state against the B beam entries in heap-array order (S:437-446, exact double chain), then
+// warp 0 rebuilds the beam by replaying the reference's min-heap insertions over the K scores
+// (S:167-211) — the array layout of the heap is observable (next step scans slots in order with
+// strict '>', the end scan of S:376-381 looks at slot 1 and slots B/2+2..B only), so the set of
+// the top-B alone is not enough.
+//
+// The per-entry payload T3_State (S:55) is not carried in the heap: every step's predecessor
+// state psi_j[i] goes to the backpointer store and the payload is recovered by walking it back
+// from the end state, which is what the payload recursion of S:359-368 / S:448 computes forward.
+//   S: = /root/reference/src/FLASH_BS_Viterbi_multithread.c
+#include "flashv_internal.h"
+#include "trellis_common.cuh"
+
+namespace flashv {
+
+// Floyd sift of S:96-123 for one node; hv/hs are 0-based images of heap slots 1..total.
+__device__ __forceinline__ void heap_sift_held(float *hv, int *hs, int total, int parent, float v, int st)
+{
+    int child = 2 * parent;
+    while (child <= total) {
+        float cv = hv[child - 1];
+        if (child + 1 <= total) {
+            float rv = hv[child];
+            if (cv > rv) ++child, cv = rv;
+        }
+        if (v <= cv) break;  // S:114 / S:152: ties stop the sift
+        hv[parent - 1] = cv;
+        hs[parent - 1] = hs[child - 1];
+        parent = child;
+        child *= 2;
+    }
+    hv[parent - 1] = v;
+    hs[parent - 1] = st;
+}
+
+// Replay of generate_state_heap() (S:167-211) over score[0..K-1] by one warp.
+//   i < B      : slot i+1 <- (score_i, i)                       S:172-179
+//   i == B-1   : Floyd heapify                                   S:180-190
+//   i >= B     : if score_i > H[1].Value replace root + sift     S:193-203
+// Nodes of one depth have disjoint subtrees, so Floyd's node = total/2..1 order is reproduced by
+// doing depths deepest-first with the nodes of a depth spread over lanes.  The streaming part
+// ballots 32 scores at a time against the current minimum (which only grows), so lanes only
+// serialise on entries that can still enter.
+__device__ void heap_replay_warp(const float *score, int K, int B, float *hv, int *hs, int lane)
+{
+    for (int s = lane; s < B; s += 32) hv[s] = score[s], hs[s] = s;
+    __syncwarp();
+    const int last_parent = B / 2;
+    if (last_parent >= 1) {
+        int depth = 31 - __clz(last_parent);
+        for (; depth >= 0; --depth) {
+            const int lo = 1 << depth;
+            const int hi = min((2 << depth) - 1, last_parent);
+            for (int node = lo + lane; node <= hi; node += 32) heap_sift_held(hv, hs, B, node, hv[node - 1], hs[node - 1]);
+            __syncwarp();
+        }
+    }
+    float mn = hv[0];
+    for (int base = B; base < K; base += 32) {
+        const int i = base + lane;
+        const float s = i < K ? score[i] : -INFINITY;
+        unsigned enter = __ballot_sync(FULL_MASK, s > mn);
+        while (enter) {
+            const int l = __ffs(enter) - 1;
+            enter &= enter - 1;
+            const float sv = __shfl_sync(FULL_MASK, s, l);
+            if (sv > mn) {  // S:193, against the minimum as it is now
+                if (lane == 0) heap_sift_held(hv, hs, B, 1, sv, base + l);
+                __syncwarp();
+                mn = hv[0];
+            }
+        }
+    }
+    __syncwarp();
+}
+
+struct BsArgs {
+    const double *LAd, *LBd, *LPi;
+    const float *LBf;
+    int K, Kp, B, T;
+    const VecDesc *vecs;
+    int nvec;
+    const int32_t *ob;
+    int32_t *ans;
+    float *score;
+    void *psi;
+    int psi16;
+    const uint8_t *ismid;
+};
+
+// dynamic shared memory: float sscore[Kp]; float hv[2][B]; int hs[2][B]
+__global__ void __launch_bounds__(1024) k_bs_pass(const BsArgs a)
+{
+    extern __shared__ float smem_f[];
+    const int K = a.K, B = a.B, T = a.T;
+    float *sscore = smem_f;
+    float *hv0 = smem_f + a.Kp;
+    int *hs0 = reinterpret_cast<int *>(hv0 + 2 * B);
+    const int v = blockIdx.x;
+    if (v >= a.nvec) return;
+    const VecDesc vd = a.vecs[v];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t *ob = a.ob + (size_t)vd.seq * T;
+    int32_t *ans = a.ans + (size_t)vd.seq * T;
+
+    // start vector, S:411-426 (S:314-320 for the first pass).  prev < 0 is the reference's
+    // vit->A[-1][i], which aliases Pi[i].
+    {
+        const int prev = vd.L == 0 ? -1 : ans[vd.L - 1];
+        const int o = ob[vd.L];
+        for (int i = tid; i < K; i += nthr) {
+            const double head = prev < 0 ? a.LPi[i] : a.LAd[(size_t)prev * K + i];
+            sscore[i] = __double2float_rn(__dadd_rn(head, a.LBd[(size_t)o * K + i]));
+        }
+    }
+    __syncthreads();
+    int cur = 0;
+    if (warp == 0) heap_replay_warp(sscore, K, B, hv0, hs0, lane);
+    __syncthreads();
+
+    for (int j = vd.L + 1; j <= vd.R; ++j) {
+        const float *hv = hv0 + cur * B;
+        const int *hs = hs0 + cur * B;
+        const int o = ob[j];
+        const bool keep = j >= vd.mid + 1;  // S:448: payload latches at j == mid+1
+        for (int i = tid; i < K; i += nthr) {
+            const float tmp = __ldg(a.LBf + (size_t)o * a.Kp + i);  // S:439
+            float best = -FLT_MAX;
+            int arg = -1;
+            for (int c = 0; c < B; ++c) {  // S:440-446, slots in array order, strict '>'
+                const float pre = __fadd_rn(tmp, hv[c]);
+                const float x = exact_cand(pre, __ldg(a.LAd + (size_t)hs[c] * K + i));
+                if (x > best) best = x, arg = c;
+            }
+            sscore[i] = best;
+            if (keep) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + i, arg < 0 ? -1 : hs[arg]);
+        }
+        __syncthreads();
+        if (warp == 0) heap_replay_warp(sscore, K, B, hv0 + (cur ^ 1) * B, hs0 + (cur ^ 1) * B, lane);
+        __syncthreads();
+        cur ^= 1;
+    }
+
+    if (tid == 0) {
+        const float *hv = hv0 + cur * B;
+        const int *hs = hs0 + cur * B;
+        int state;
+        if (vd.flags & VEC_FULL_RANGE) {  // S:374-383 / S:454-463
+            float sc = hv[0];
+            int arg = 0;
+            for (int c = B / 2 + 1; c < B; ++c)
+                if (hv[c] > sc) arg = c, sc = hv[c];
+            state = hs[arg];
+            ans[vd.R] = state;
+            a.score[vd.seq] = sc;
+        } else {  // Find_T3_State, S:73-86: -1 when Ans[R] fell out of the beam
+            const int want = ans[vd.R];
+            state = -1;
+            for (int c = 0; c < B; ++c)
+                if (hs[c] == want) {
+                    state = want;
+                    break;
+                }
+        }
+        for (int j = vd.R; j >= vd.mid + 1; --j) {
+            if (state >= 0) state = psi_load(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + state);
+            if ((vd.flags & VEC_FIRST_PASS) && a.ismid[j - 1]) ans[j - 1] = state;
+        }
+        if (!(vd.flags & VEC_FIRST_PASS)) ans[vd.mid] = state;
+    }
+}
+
+static size_t bs_smem_bytes(int Kp, int B) { return (size_t)Kp * 4 + (size_t)B * 16; }
+
+int bs_run_pass(flashv_plan *p, const Pass &pass)
+{
+    flashv_model *m = p->model;
+    flashv_ctx *ctx = m->ctx;
+    BsArgs a;
+    a.LAd = m->LAd, a.LBd = m->LBd, a.LPi = m->LPi, a.LBf = m->LBf;
+    a.K = m->K, a.Kp = m->Kp, a.B = p->B, a.T = p->T;
+    a.vecs = p->d_vecs + pass.vec_offset, a.nvec = pass.nvec;
+    a.ob = p->d_ob, a.ans = p->d_ans, a.score = p->d_score;
+    a.psi = p->d_psi, a.psi16 = p->psi16, a.ismid = p->d_ismid;
+    const size_t smem = bs_smem_bytes(m->Kp, p->B);
+    if (smem > (size_t)ctx->smem_optin) {
+        set_error("FLASH-BS: K=%d, B=%d needs %zu bytes of shared memory per CTA (limit %d)", m->K, p->B, smem,
+                  ctx->smem_optin);
+        return FLASHV_ERR_ARG;
+    }
+    FV_CUDA(cudaFuncSetAttribute(k_bs_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bs_pass<<<pass.nvec, 1024, smem, ctx->stream>>>(a);
+    FV_CUDA(cudaGetLastError());
+    ++p->launches;
+    return FLASHV_OK;
+}
+
+// ---- single-step hooks for the parity tests ---------------------------------------------------
+__global__ void __launch_bounds__(256) k_bs_score_once(const double *__restrict__ LAd, const float *__restrict__ LBf,
+                                                       int K, int Kp, const float *__restrict__ hv,
+                                                       const int32_t *__restrict__ hs, int B, int o,
+                                                       float *__restrict__ score, int32_t *__restrict__ arg_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    const float tmp = LBf[(size_t)o * Kp + i];
+    float best = -FLT_MAX;
+    int arg = -1;
+    for (int c = 0; c < B; ++c) {
+        const float pre = __fadd_rn(tmp, hv[c]);
+        const float x = exact_cand(pre, LAd[(size_t)hs[c] * K + i]);
+        if (x > best) best = x, arg = c;
+    }
+    score[i] = best;
+    arg_out[i] = arg;
+}
+
+__global__ void k_bs_replay_once(const float *__restrict__ score, int K, int B, float *hv_out, int32_t *hs_out)
+{
+    extern __shared__ float smem_f[];
+    float *hv = smem_f;
+    int *hs = reinterpret_cast<int *>(smem_f + B);
+    heap_replay_warp(score, K, B, hv, hs, threadIdx.x);
+    for (int s = threadIdx.x; s < B; s += 32) hv_out[s] = hv[s], hs_out[s] = hs[s];
+}
+
+int bs_single_score(flashv_model *m, const float *hv_dev, const int32_t *hs_dev, int B, int o, float *score_dev,
+                    int32_t *arg_dev)
+{
+    k_bs_score_once<<<(m->K + 255) / 256, 256, 0, m->ctx->stream>>>(m->LAd, m->LBf, m->K, m->Kp, hv_dev, hs_dev, B, o,
+                                                                  score_dev, arg_dev);
+    FV_CUDA(cudaGetLastError());
+    return FLASHV_OK;
+}
+
+int bs_single_replay(flashv_ctx *ctx, const float *score_dev, int K, int B, float *hv_dev, int32_t *hs_dev)
+{
+    const size_t smem = (size_t)B * 8;
+    FV_CUDA(cudaFuncSetAttribute(k_bs_replay_once, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bs_replay_once<<<1, 32, smem, ctx->stream>>>(score_dev, K, B, hv_dev, hs_dev);
+    FV_CUDA(cudaGetLastError());
+    return FLASHV_OK;
+}
+
+}  // namespace flashv

@@ -1,0 +1,290 @@
+// flash_kernels.cu — FLASH passes on the device: start vectors, the per-step max-plus kernel
+// (engine STEP), end-state selection and the non-recursive backtrack.
+//
+// A "pass" advances a set of independent trellis vectors in lock-step: the N-way first pass
+// (nvviterNdivide, F:126-202; one vector per sequence) or one level of the task tree (nvviter,
+// F:204-262; one vector per task per sequence).  Instead of composing tracker tables every step
+// (F:176-179, F:242: (N-1)*K gathers per step), the kernels append each step's backpointer row to
+// an HBM store and one thread per vector walks it backwards afterwards; composing T2 forward and
+// walking psi backward give the same state by construction (T2_j[i] = T2_{j-1}[psi_j[i]]).
+//   F: = /root/reference/src/FLASH_Viterbi_multithread.c
+#include "flashv_internal.h"
+#include "trellis_common.cuh"
+
+namespace flashv {
+
+// ---- start vectors: F:142 / F:212 (pi form) and F:150 / F:220 (restart from Ans[L-1]) ------
+__global__ void k_flash_init(const VecDesc *__restrict__ vecs, int nvec, const int32_t *__restrict__ ob,
+                             const int32_t *__restrict__ ans, int T, const double *__restrict__ LAd,
+                             const double *__restrict__ LBd, const double *__restrict__ LPi, int K, int Kp,
+                             float *__restrict__ delta)
+{
+    const int v = blockIdx.y;
+    if (v >= nvec) return;
+    const VecDesc vd = vecs[v];
+    const int prev = vd.L == 0 ? -1 : ans[(size_t)vd.seq * T + vd.L - 1];
+    const int o = ob[(size_t)vd.seq * T + vd.L];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
+        const double head = prev < 0 ? LPi[i] : LAd[(size_t)prev * K + i];
+        delta[(size_t)v * Kp + i] = __double2float_rn(__dadd_rn(head, LBd[(size_t)o * K + i]));
+    }
+}
+
+// ---- engine STEP: one launch per trellis step ------------------------------------------------
+// grid.x: blocks of 8 destination columns (one per warp); grid.y: groups of QB vectors.
+// A warp owns column i: lane l reads hiT[i][4*(l+32u) .. +3] as one 128-bit load per u, so the
+// warp streams the column as contiguous 512-byte requests; delta of the group's vectors sits in
+// shared memory.  Per update: FADD, FADD, FMNMX (estimate only); the exact value is recovered by
+// resolve_column() for the handful of candidates inside the window.
+struct StepArgs {
+    const float *hiT;
+    const double *LAd;
+    const float *LBf;
+    int K, Kp;
+    const VecDesc *vecs;
+    int nact, s;
+    const float *din;
+    float *dout;
+    const int32_t *ob;
+    int T;
+    void *psi;
+    int psi16;
+};
+
+template <int QB>
+__global__ void __launch_bounds__(256) k_flash_step(const StepArgs a)
+{
+    extern __shared__ float4 sdelta4[];
+    const int Kp4 = a.Kp >> 2;
+    const int v0 = blockIdx.y * QB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+        const bool live = v0 + q < a.nact;
+        const float4 *src = reinterpret_cast<const float4 *>(a.din + (size_t)(v0 + q) * a.Kp);
+        for (int t = tid; t < Kp4; t += 256) sdelta4[q * Kp4 + t] = live ? src[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= a.K) return;
+
+    float tmp[QB];
+    int jj[QB];
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+        tmp[q] = 0.f, jj[q] = 0;
+        if (v0 + q < a.nact) {
+            const VecDesc vd = a.vecs[v0 + q];
+            jj[q] = vd.L + a.s;
+            tmp[q] = __ldg(a.LBf + (size_t)a.ob[(size_t)vd.seq * a.T + jj[q]] * a.Kp + i);  // F:167
+        }
+    }
+    float cm[QB][4];
+#pragma unroll
+    for (int q = 0; q < QB; ++q) cm[q][0] = cm[q][1] = cm[q][2] = cm[q][3] = -INFINITY;
+
+    const float4 *col4 = reinterpret_cast<const float4 *>(a.hiT + (size_t)i * a.Kp);
+#pragma unroll 4
+    for (int t = lane; t < Kp4; t += 32) {
+        const float4 h = __ldg(col4 + t);
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+            const float4 d = sdelta4[q * Kp4 + t];
+            cm[q][0] = fmaxf(cm[q][0], __fadd_rn(__fadd_rn(tmp[q], d.x), h.x));
+            cm[q][1] = fmaxf(cm[q][1], __fadd_rn(__fadd_rn(tmp[q], d.y), h.y));
+            cm[q][2] = fmaxf(cm[q][2], __fadd_rn(__fadd_rn(tmp[q], d.z), h.z));
+            cm[q][3] = fmaxf(cm[q][3], __fadd_rn(__fadd_rn(tmp[q], d.w), h.w));
+        }
+    }
+    const float *col = a.hiT + (size_t)i * a.Kp;
+    const float *sdelta = reinterpret_cast<const float *>(sdelta4);
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+        if (v0 + q >= a.nact) continue;  // warp-uniform
+        const Best b = resolve_column(cm[q], tmp[q], col, sdelta + (size_t)q * a.Kp, a.LAd, a.K, a.Kp, i, lane);
+        if (lane == 0) {
+            a.dout[(size_t)(v0 + q) * a.Kp + i] = b.x;
+            const VecDesc vd = a.vecs[v0 + q];
+            if (jj[q] >= vd.mid + 1)  // F:242: only steps from the latch on are ever read back
+                psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (jj[q] - vd.mid - 1)) * a.K + i, b.k);
+        }
+    }
+}
+
+// ---- end of a full-range pass: Ans[T-1] = first argmax of delta (F:188-195, F:251-258) ----
+__global__ void __launch_bounds__(256) k_flash_end(const VecDesc *__restrict__ vecs, int nvec,
+                                                   const float *__restrict__ delta, int K, int Kp, int T,
+                                                   int32_t *__restrict__ ans, float *__restrict__ score,
+                                                   int32_t *__restrict__ endstate)
+{
+    const int v = blockIdx.x;
+    if (v >= nvec) return;
+    const VecDesc vd = vecs[v];
+    __shared__ float sx[8];
+    __shared__ int sk[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (vd.flags & VEC_FULL_RANGE) {
+        // "score = T1[cur][0]; arg = 0; if (T1[cur][i] > score)": first maximum, index 0 if all equal.
+        Best b{-INFINITY, 0x7fffffff};
+        for (int i = tid; i < K; i += 256) {
+            float x = delta[(size_t)v * Kp + i];
+            if (x > b.x || (x == b.x && i < b.k)) b.x = x, b.k = i;
+        }
+        b = warp_best(b);
+        if (lane == 0) sx[warp] = b.x, sk[warp] = b.k;
+        __syncthreads();
+        if (tid == 0) {
+            Best r{sx[0], sk[0]};
+            for (int w = 1; w < 8; ++w) best_take(r, sx[w], sk[w]);
+            if (r.k == 0x7fffffff) r.k = 0;  // every entry -inf: the reference keeps arg = 0
+            ans[(size_t)vd.seq * T + vd.R] = r.k;
+            score[vd.seq] = delta[(size_t)v * Kp + r.k];
+            endstate[v] = r.k;
+        }
+    } else if (tid == 0) {
+        endstate[v] = ans[(size_t)vd.seq * T + vd.R];  // F:248
+    }
+}
+
+// ---- non-recursive backtrack through the stored rows --------------------------------------
+// One thread per vector: state_{j-1} = psi_j[state_j] for j = R .. mid+1.  A task records
+// Ans[mid] (F:261); the first pass records every segment boundary it walks over (F:198-201).
+__global__ void k_flash_backtrack(const VecDesc *__restrict__ vecs, int nvec, const void *__restrict__ psi, int psi16,
+                                  int K, int T, const uint8_t *__restrict__ ismid,
+                                  const int32_t *__restrict__ endstate, int32_t *__restrict__ ans)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvec) return;
+    const VecDesc vd = vecs[v];
+    int state = endstate[v];
+    int32_t *out = ans + (size_t)vd.seq * T;
+    for (int j = vd.R; j >= vd.mid + 1; --j) {
+        if (state >= 0) state = psi_load(psi, psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + state);
+        if ((vd.flags & VEC_FIRST_PASS) && ismid[j - 1]) out[j - 1] = state;
+    }
+    if (!(vd.flags & VEC_FIRST_PASS)) out[vd.mid] = state;
+}
+
+// ---- host orchestration -------------------------------------------------------------------------
+template <int QB>
+static cudaError_t launch_step(const StepArgs &a, int nact, cudaStream_t st)
+{
+    const size_t smem = (size_t)QB * a.Kp * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_flash_step<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((a.K + 7) / 8, (nact + QB - 1) / QB);
+    k_flash_step<QB><<<grid, 256, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+static int pick_qb(int nact, int Kp)
+{
+    // delta of QB vectors must fit in shared memory next to a second resident CTA
+    int cap = (96 * 1024) / (Kp * 4);
+    int qb = 1;
+    while (qb * 2 <= 4 && qb * 2 <= cap && qb * 2 <= nact) qb *= 2;
+    return qb;
+}
+
+int persistent_pass(flashv_plan *p, const Pass &pass);  // flash_persistent.cu
+
+int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
+{
+    flashv_model *m = p->model;
+    flashv_ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const int K = m->K, Kp = m->Kp, T = p->T;
+    const VecDesc *vecs = p->d_vecs + pass.vec_offset;
+    float *d0 = p->d_delta, *d1 = p->d_delta + (size_t)p->max_vec * Kp;
+
+    if (time_it) FV_CUDA(cudaEventRecord(ctx->ev[2], st));
+    dim3 ig((K + 255) / 256, pass.nvec);
+    k_flash_init<<<ig, 256, 0, st>>>(vecs, pass.nvec, p->d_ob, p->d_ans, T, m->LAd, m->LBd, m->LPi, K, Kp, d0);
+    FV_CUDA(cudaGetLastError());
+    ++p->launches;
+
+    const float *final_delta = d0;
+    const bool persistent = p->engine == FLASHV_ENGINE_PERSISTENT && pass.nvec == 1;
+    if (persistent) {
+        int rc = persistent_pass(p, pass);
+        if (rc != FLASHV_OK) return rc;
+        final_delta = (pass.max_steps & 1) ? d1 : d0;
+    } else {
+        for (int s = 1; s <= pass.max_steps; ++s) {
+            StepArgs a;
+            a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = K, a.Kp = Kp;
+            a.vecs = vecs, a.nact = pass.nactive[s], a.s = s;
+            a.din = (s & 1) ? d0 : d1, a.dout = (s & 1) ? d1 : d0;
+            a.ob = p->d_ob, a.T = T, a.psi = p->d_psi, a.psi16 = p->psi16;
+            cudaError_t e;
+            switch (pick_qb(a.nact, Kp)) {
+                case 4: e = launch_step<4>(a, a.nact, st); break;
+                case 2: e = launch_step<2>(a, a.nact, st); break;
+                default: e = launch_step<1>(a, a.nact, st); break;
+            }
+            FV_CUDA(e);
+            ++p->launches;
+        }
+        final_delta = (pass.max_steps & 1) ? d1 : d0;
+    }
+    if (time_it) FV_CUDA(cudaEventRecord(ctx->ev[3], st));
+
+    // Only full-range vectors read delta here, and they run all max_steps steps of the pass.
+    k_flash_end<<<pass.nvec, 256, 0, st>>>(vecs, pass.nvec, final_delta, K, Kp, T, p->d_ans, p->d_score, p->d_endstate);
+    FV_CUDA(cudaGetLastError());
+    k_flash_backtrack<<<(pass.nvec + 127) / 128, 128, 0, st>>>(vecs, pass.nvec, p->d_psi, p->psi16, K, T, p->d_ismid,
+                                                               p->d_endstate, p->d_ans);
+    FV_CUDA(cudaGetLastError());
+    p->launches += 2;
+    return FLASHV_OK;
+}
+
+// ---- single-step hooks for the per-step parity tests ------------------------------------------
+int persistent_single_step(flashv_model *m, const float *d_in_dev, int o, float *d_out_dev, int32_t *psi_dev);
+
+__global__ void k_one_vec(VecDesc *v, int32_t *ob, int o)
+{
+    v->seq = 0, v->L = 0, v->R = 1, v->mid = 0, v->psi_row = 0, v->flags = 0;
+    ob[0] = o, ob[1] = o;
+}
+
+int flash_single_step(flashv_model *m, const float *d_in_dev, int o, float *d_out_dev, int32_t *psi_dev, int engine)
+{
+    if (engine == FLASHV_ENGINE_PERSISTENT) return persistent_single_step(m, d_in_dev, o, d_out_dev, psi_dev);
+    flashv_ctx *ctx = m->ctx;
+    // a 1-vector, 1-step pass: L=0, R=1, mid=0 so the step at j=1 stores its backpointers in row 0
+    VecDesc *dv = reinterpret_cast<VecDesc *>(m->scratch_i);
+    int32_t *dob = m->scratch_i + 16;
+    k_one_vec<<<1, 1, 0, ctx->stream>>>(dv, dob, o);
+    FV_CUDA(cudaGetLastError());
+    StepArgs a;
+    a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+    a.vecs = dv, a.nact = 1, a.s = 1, a.din = d_in_dev, a.dout = d_out_dev;
+    a.ob = dob, a.T = 2, a.psi = psi_dev, a.psi16 = 0;
+    FV_CUDA(launch_step<1>(a, 1, ctx->stream));
+    return FLASHV_OK;
+}
+
+int flash_single_init(flashv_model *m, int prev_state, int o, float *d_out_dev)
+{
+    flashv_ctx *ctx = m->ctx;
+    // L == 0 selects the pi form; otherwise ans[L-1] must hold prev_state: use L=1 and a 2-entry ans
+    VecDesc hv{0, prev_state < 0 ? 0 : 1, 1, 0, 0, 0};
+    int32_t hob[2] = {o, o}, hans[2] = {prev_state, 0};
+    VecDesc *dv = reinterpret_cast<VecDesc *>(m->scratch_i);
+    int32_t *dob = m->scratch_i + 16, *dans = m->scratch_i + 24;
+    FV_CUDA(cudaMemcpyAsync(dv, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx->stream));
+    FV_CUDA(cudaMemcpyAsync(dob, hob, sizeof(hob), cudaMemcpyHostToDevice, ctx->stream));
+    FV_CUDA(cudaMemcpyAsync(dans, hans, sizeof(hans), cudaMemcpyHostToDevice, ctx->stream));
+    FV_CUDA(cudaStreamSynchronize(ctx->stream));  // host arrays are on this frame
+    k_flash_init<<<dim3((m->K + 255) / 256, 1), 256, 0, ctx->stream>>>(dv, 1, dob, dans, 2, m->LAd, m->LBd, m->LPi, m->K,
+                                                                      m->Kp, d_out_dev);
+    FV_CUDA(cudaGetLastError());
+    return FLASHV_OK;
+}
+
+}  // namespace flashv

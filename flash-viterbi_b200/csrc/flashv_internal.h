@@ -1,0 +1,140 @@
+// flashv_internal.h — shared declarations of the libflashv translation units.
+// Not part of the ABI (include/flashv.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "flashv.h"
+
+namespace flashv {
+
+// ---- error plumbing --------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define FV_CUDA(call)                                                          \
+    do {                                                                       \
+        cudaError_t fv_e_ = (call);                                            \
+        if (fv_e_ != cudaSuccess) return ::flashv::cuda_fail(fv_e_, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// ---- schedule (host, pure function of T and N) -----------------------------------------
+struct Task {
+    int L, R, mid;
+};
+
+// The reference's FIFO (F:284-304, F:349-359) flattened into tree levels: every task of level
+// l+1 is a child of a task of level l, and tasks of one level are independent (each reads only
+// Ans[] entries written by its ancestors), so a level advances in lock-step on the device.
+struct Schedule {
+    int T = 0, N = 0;
+    bool first_pass = false;   // F:342
+    std::vector<int> mids;     // F:129-136, N-1 entries when first_pass
+    std::vector<Task> fifo;    // queue order, exactly the tasks the reference runs
+    std::vector<std::vector<Task>> levels;  // same tasks, grouped by depth, longest first
+    long long executed_steps = 0;
+};
+// returns false for the domain the reference mishandles (T < 2, N < 1, T == 2N with N > 2)
+bool build_schedule(int T, int N, Schedule *out);
+int pool_struct_bytes(int N);
+
+// ---- device-side descriptors -------------------------------------------------------------
+// One trellis vector in flight: sequence `seq` walking the interval (L,R).  Backpointers are
+// kept only for steps j >= mid+1 (F:242: the tracker latches at j == mid+1), in rows
+// psi_row .. psi_row + (R-mid-1) of the pass's backpointer store.
+struct VecDesc {
+    int seq, L, R, mid;
+    int psi_row;
+    int flags;
+};
+enum : int {
+    VEC_FULL_RANGE = 1,   // (L,R) == (0,T-1): the pass also picks Ans[T-1] (F:186-196, F:249-259)
+    VEC_FIRST_PASS = 2,   // nvviterNdivide: record every segment boundary on the way back (F:198-201)
+};
+
+struct Pass {
+    int nvec = 0;        // vectors (tasks of the level x batch), sorted by steps descending
+    int max_steps = 0;   // max (R-L)
+    int psi_rows = 0;    // rows of the backpointer store this pass needs
+    size_t vec_offset = 0;  // into the plan's device VecDesc array
+    std::vector<int> nactive;  // nactive[s] = vectors still stepping at step s (1-based), prefix of the order
+    bool full_range = false;
+    VecDesc first_vec{};  // host copy of vector 0 (single-vector passes are driven from it)
+};
+
+}  // namespace flashv
+
+struct flashv_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    int smem_optin = 0;
+    int coop = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // pinned staging for the one-call API
+    int32_t *h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+};
+
+struct flashv_model {
+    flashv_ctx *ctx = nullptr;
+    int K = 0, M = 0;
+    int Kp = 0;               // K rounded up to a multiple of 128 (one warp x float4)
+    float *hiT = nullptr;     // [K][Kp]  (float)log A, destination-major: hiT[i][k] = log A[k][i]; pad = -inf
+    double *LAd = nullptr;    // [K][K]   log A, source-major as the reference stores A (F:27)
+    float *LBf = nullptr;     // [M][Kp]  (float)log B, symbol-major: LBf[o][i] — the per-step "tmp" (F:167)
+    double *LBd = nullptr;    // [M][K]   log B (double), symbol-major — start vectors (F:142, F:220)
+    double *LPi = nullptr;    // [K]      log Pi
+    float *scratch_f = nullptr;   // test hooks: 2*Kp floats
+    int32_t *scratch_i = nullptr; // test hooks: Kp ints
+    size_t bytes = 0;
+    double prep_ms = 0;
+    std::vector<flashv_plan *> plan_cache;  // owned; used by the one-call decodes
+};
+
+struct flashv_plan {
+    flashv_model *model = nullptr;
+    int T = 0, N = 0, batch = 0, B = 0, engine = 0;
+    flashv::Schedule sched;
+    std::vector<flashv::Pass> passes;  // [0] = first pass when sched.first_pass, then one per level
+    int max_vec = 0;
+    int psi16 = 0;
+    // device
+    int32_t *d_ob = nullptr;      // [batch][T]
+    int32_t *d_ans = nullptr;     // [batch][T]
+    float *d_score = nullptr;     // [batch]
+    float *d_delta = nullptr;     // [2][max_vec][Kp]
+    void *d_psi = nullptr;        // [max psi_rows][K] u16 or i32
+    flashv::VecDesc *d_vecs = nullptr;
+    uint8_t *d_ismid = nullptr;   // [T] 1 where a first-pass segment boundary sits
+    int32_t *d_endstate = nullptr;  // [max_vec]
+    unsigned int *d_sync = nullptr; // grid-barrier words of the persistent engine
+    // FLASH-BS
+    float *d_bs_score = nullptr;  // [max_vec][Kp]
+    size_t bytes = 0;
+    // last run
+    flashv_report rep{};
+    bool uploaded = false, ran = false;
+    int launches = 0;
+};
+
+// ---- kernels / stages (defined in the .cu files) -------------------------------------------
+namespace flashv {
+
+int tables_build(flashv_model *m, const float *A, const float *B, const float *Pi);
+
+int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it);
+int bs_run_pass(flashv_plan *p, const Pass &pass);
+
+int flash_single_step(flashv_model *m, const float *d_in_dev, int o, float *d_out_dev, int32_t *psi_dev, int engine);
+int flash_single_init(flashv_model *m, int prev_state, int o, float *d_out_dev);
+int bs_single_score(flashv_model *m, const float *hv_dev, const int32_t *hs_dev, int B, int o, float *score_dev,
+                    int32_t *arg_dev);
+int bs_single_replay(flashv_ctx *ctx, const float *score_dev, int K, int B, float *hv_dev, int32_t *hs_dev);
+
+}  // namespace flashv

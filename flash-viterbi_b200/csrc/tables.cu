@@ -1,0 +1,174 @@
+// tables.cu — log tables of one HMM: host libm -> device layouts.
+//
+// The reference calls libm log() inside its innermost loop (F:170; also F:142,150,167,212,220,
+// 233,236).  glibc's log is not correctly rounded and CUDA's differs from it in the last bit on
+// some inputs, so a bit-exact decoder must take its logarithms from the same host libm the
+// reference links.  They depend only on the model, so they are computed ONCE here (all host
+// cores), uploaded, and re-laid-out on the device:
+//   LAd [k][i] double  source-major, as the reference stores A (F:27): exact re-evaluation and
+//                      start vectors (F:220 reads row Ans[L-1])
+//   hiT [i][k] float   destination-major, padded to Kp: the stream the trellis kernels read —
+//                      the max over k for one destination i is one contiguous run
+//   LBf [o][i] float   the per-step "tmp" (F:167), symbol-major so one step reads one row
+//   LBd [o][i] double  start vectors (F:142, F:220)
+//   LPi [i]    double
+//   F: = /root/reference/src/FLASH_Viterbi_multithread.c
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
+#include <thread>
+#include <vector>
+
+#include "flashv_internal.h"
+
+namespace flashv {
+
+// hiT[i][k] = (float)LAd[k][i] for k < K, -inf in the padding; 32x32 tiles through shared memory
+// so both the double reads (along i) and the float writes (along k) are coalesced.
+__global__ void k_transpose_to_f32(const double *__restrict__ LAd, float *__restrict__ hiT, int K, int Kp)
+{
+    __shared__ float tile[32][33];
+    const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int k = k0 + r, i = i0 + threadIdx.x;
+        float v = -INFINITY;
+        if (k < K && i < K) v = __double2float_rn(LAd[(size_t)k * K + i]);
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int i = i0 + r, k = k0 + threadIdx.x;
+        if (i < K && k < Kp) hiT[(size_t)i * Kp + k] = tile[threadIdx.x][r];
+    }
+}
+
+static bool in_unit(const float *p, size_t n)
+{
+    for (size_t i = 0; i < n; ++i)
+        if (!(p[i] >= 0.0f && p[i] <= 1.0f)) return false;
+    return true;
+}
+
+int tables_build(flashv_model *m, const float *A, const float *B, const float *Pi)
+{
+    const int K = m->K, M = m->M, Kp = m->Kp;
+    flashv_ctx *ctx = m->ctx;
+    auto t0 = std::chrono::steady_clock::now();
+
+    // The window filter of the trellis kernels relies on every log being <= 0;
+    // anything else is not a probability table.  The reference would decode garbage or NaN.
+    if (!in_unit(A, (size_t)K * K) || !in_unit(B, (size_t)K * M) || !in_unit(Pi, (size_t)K)) {
+        set_error("flashv_model_create: A/B/Pi entries must be finite and inside [0,1]");
+        return FLASHV_ERR_DOMAIN;
+    }
+
+    const size_t nA = (size_t)K * K;
+    double *hLA = nullptr;
+    if (cudaMallocHost(&hLA, nA * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("flashv_model_create: pinned allocation of %zu bytes failed", nA * sizeof(double));
+        return FLASHV_ERR_NOMEM;
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    int nthr = (int)(hw ? hw : 8);
+    if (nthr > 64) nthr = 64;
+    if ((size_t)nthr > (size_t)K) nthr = K;
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthr; ++t)
+            pool.emplace_back([=]() {
+                for (int k = t; k < K; k += nthr) {
+                    const float *src = A + (size_t)k * K;
+                    double *dst = hLA + (size_t)k * K;
+                    for (int i = 0; i < K; ++i) dst[i] = log((double)src[i]);  // F:170
+                }
+            });
+        for (auto &th : pool) th.join();
+    }
+    std::vector<double> hLB((size_t)M * K), hLPi((size_t)K);
+    std::vector<float> hLBf((size_t)M * Kp, 0.0f);
+    for (int i = 0; i < K; ++i) {
+        for (int o = 0; o < M; ++o) {
+            double v = log((double)B[(size_t)i * M + o]);  // F:142 / F:167
+            hLB[(size_t)o * K + i] = v;
+            hLBf[(size_t)o * Kp + i] = (float)v;  // "tmp = log(...)" stored into a float, F:167
+        }
+        hLPi[i] = log((double)Pi[i]);  // F:142
+    }
+
+    cudaError_t e;
+#define TB_CUDA(call)                                                  \
+    if ((e = (call)) != cudaSuccess) {                                 \
+        cudaFreeHost(hLA);                                             \
+        return cuda_fail(e, #call, __FILE__, __LINE__);                \
+    }
+    TB_CUDA(cudaMalloc(&m->LAd, nA * sizeof(double)));
+    TB_CUDA(cudaMalloc(&m->hiT, (size_t)K * Kp * sizeof(float)));
+    TB_CUDA(cudaMalloc(&m->LBf, (size_t)M * Kp * sizeof(float)));
+    TB_CUDA(cudaMalloc(&m->LBd, (size_t)M * K * sizeof(double)));
+    TB_CUDA(cudaMalloc(&m->LPi, (size_t)K * sizeof(double)));
+    TB_CUDA(cudaMalloc(&m->scratch_f, (size_t)4 * Kp * sizeof(float)));
+    TB_CUDA(cudaMalloc(&m->scratch_i, (size_t)2 * Kp * sizeof(int32_t)));
+    m->bytes = nA * sizeof(double) + (size_t)K * Kp * 4 + (size_t)M * Kp * 4 + (size_t)M * K * 8 + (size_t)K * 8 +
+               (size_t)6 * Kp * 4;
+    TB_CUDA(cudaMemcpyAsync(m->LAd, hLA, nA * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(cudaMemcpyAsync(m->LBf, hLBf.data(), hLBf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(cudaMemcpyAsync(m->LBd, hLB.data(), hLB.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(cudaMemcpyAsync(m->LPi, hLPi.data(), hLPi.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(cudaMemsetAsync(m->scratch_f, 0, (size_t)4 * Kp * sizeof(float), ctx->stream));
+    dim3 grid((K + 31) / 32, (Kp + 31) / 32), block(32, 8);
+    k_transpose_to_f32<<<grid, block, 0, ctx->stream>>>(m->LAd, m->hiT, K, Kp);
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef TB_CUDA
+    cudaFreeHost(hLA);
+    m->prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return FLASHV_OK;
+}
+
+}  // namespace flashv
+
+// Program-shell ingest, F:56-95: every probability goes through fscanf("%f") into a float, i.e.
+// strtof — one rounding from the decimal text.  Read the file whole and walk it with strtof.
+static long read_text(const char *path, long n, float *fout, int32_t *iout)
+{
+    FILE *fp = fopen(path, "rb");
+    if (!fp) {
+        flashv::set_error("cannot open %s", path);
+        return FLASHV_ERR_ARG;
+    }
+    fseek(fp, 0, SEEK_END);
+    long size = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    char *buf = (char *)malloc((size_t)size + 1);
+    if (!buf) {
+        fclose(fp);
+        flashv::set_error("out of memory reading %s", path);
+        return FLASHV_ERR_NOMEM;
+    }
+    size_t got = fread(buf, 1, (size_t)size, fp);
+    fclose(fp);
+    buf[got] = 0;
+    long cnt = 0;
+    char *p = buf, *end = nullptr;
+    while (cnt < n) {
+        if (fout) {
+            float v = strtof(p, &end);
+            if (end == p) break;
+            fout[cnt] = v;
+        } else {
+            long v = strtol(p, &end, 10);
+            if (end == p) break;
+            iout[cnt] = (int32_t)v;
+        }
+        p = end;
+        ++cnt;
+    }
+    free(buf);
+    return cnt;
+}
+
+extern "C" long flashv_read_floats_text(const char *path, long n, float *out) { return read_text(path, n, out, nullptr); }
+extern "C" long flashv_read_ints_text(const char *path, long n, int32_t *out) { return read_text(path, n, nullptr, out); }

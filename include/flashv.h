@@ -1,0 +1,131 @@
+/*
+ * flashv.h — C ABI of the B200-native FLASH / FLASH-BS Viterbi decoder (libflashv.so).
+ *
+ * Drop-in boundary for the reference's hot path.  The reference exports no library symbol:
+ * its interface is the program shell around calc().  Each entry point below
+ * names the reference function it replaces:
+ *
+ *   F: = /root/reference/src/FLASH_Viterbi_multithread.c
+ *   S: = /root/reference/src/FLASH_BS_Viterbi_multithread.c
+ *
+ * Plain C types only; all pointers are HOST pointers unless a name says "dev".  Every
+ * function returns FLASHV_OK (0) or a negative FLASHV_ERR_* code; flashv_last_error() gives
+ * the message of the last failure on the calling thread.  There is no CPU fallback: every
+ * decode runs on the CUDA device of its context or fails.
+ */
+#ifndef FLASHV_H
+#define FLASHV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLASHV_OK 0
+#define FLASHV_ERR_ARG (-1)     /* bad argument (NULL, sizes, T < 2, T == 2N with N > 2, B > K ...) */
+#define FLASHV_ERR_DOMAIN (-2)  /* A/B/Pi entry outside [0,1] or not finite */
+#define FLASHV_ERR_CUDA (-3)    /* CUDA runtime failure (message holds cudaGetErrorString) */
+#define FLASHV_ERR_NOMEM (-4)   /* host or device allocation failed */
+#define FLASHV_ERR_STATE (-5)   /* call order (run before upload, ...) */
+
+typedef struct flashv_ctx flashv_ctx;     /* one GPU + one stream + scratch; one host thread at a time */
+typedef struct flashv_model flashv_model; /* device-resident log tables of one HMM */
+typedef struct flashv_plan flashv_plan;   /* decode schedule + workspace for one (T, N, batch[, B]) */
+
+/* Which trellis engine the FLASH plan uses for single-vector passes (the N-way first pass and
+ * the root task).  Both are exact; AUTO picks the persistent kernel when the device can hold
+ * one CTA per SM co-resident. */
+#define FLASHV_ENGINE_AUTO 0
+#define FLASHV_ENGINE_STEP 1       /* one kernel launch per trellis step */
+#define FLASHV_ENGINE_PERSISTENT 2 /* one cooperative launch per pass, TMA-fed, grid barrier per step */
+
+typedef struct flashv_report {
+    double decode_ms;          /* device time of the decode proper (CUDA events, tables resident) */
+    double first_pass_ms;      /* device time of the full-length pass alone (0 if none) */
+    double h2d_ms, d2h_ms;     /* observation upload / path download, host wall clock */
+    long long executed_steps;  /* S(T,N) per sequence: (T-1 if first pass) + sum (R-L) over tasks */
+    long long device_bytes;    /* tables + plan workspace actually allocated on the device */
+    int memory_bytes;          /* the reference's "memory:" formula (F:355,364-367 / S:564,573-576) */
+    int first_pass;            /* 1 iff the N-way pass ran (F:342) */
+    int n_tasks;               /* queue tasks per sequence (T-N or T-1) */
+    int n_levels;              /* task-tree levels executed */
+    int kernel_launches;       /* kernels launched by this decode */
+    int engine;                /* FLASHV_ENGINE_* actually used for the full-length pass */
+} flashv_report;
+
+const char *flashv_last_error(void);
+const char *flashv_version(void);
+
+/* ---- context ------------------------------------------------------------------------- */
+/* stream: a cudaStream_t created by the caller on `device` (e.g. torch's), or NULL to let
+ * the context create its own non-blocking stream.  All work of the context is issued there. */
+int flashv_ctx_create(int device, void *stream, flashv_ctx **out);
+void flashv_ctx_destroy(flashv_ctx *ctx);
+void *flashv_ctx_stream(const flashv_ctx *ctx);
+int flashv_ctx_sync(flashv_ctx *ctx);
+int flashv_ctx_sm_count(const flashv_ctx *ctx);
+
+/* ---- model: replaces create_vit() (F:97-107) and the in-loop log() calls (F:142,167,170) */
+/* A[K][K] (row = source, column = destination), B[K][M], Pi[K]: the float values the
+ * reference's loader leaves in VIT (F:25-34).  Log tables are computed on the HOST with the
+ * host libm (the same log() the reference calls), then laid out on the device. */
+int flashv_model_create(flashv_ctx *ctx, int K, int M, const float *A, const float *B, const float *Pi,
+                        flashv_model **out);
+void flashv_model_destroy(flashv_model *model);
+int flashv_model_K(const flashv_model *model);
+int flashv_model_M(const flashv_model *model);
+double flashv_model_prep_ms(const flashv_model *model); /* host log tables + upload + layout */
+
+/* Program-shell loader (F:56-95): fscanf("%f") / fscanf("%d") semantics. Returns count read or <0. */
+long flashv_read_floats_text(const char *path, long n, float *out);
+long flashv_read_ints_text(const char *path, long n, int32_t *out);
+
+/* ---- one-call decodes: replace calc() ------------------------------------------------ */
+/* FLASH, calc() of F:338-368.  ob[T] in [0,M); N = MAX_THREADS (the segment count).
+ * path_out[T]; score_out (may be NULL) = max_i delta_{T-1}[i] of the full-range pass. */
+int flashv_decode(flashv_model *model, const int32_t *ob, int T, int N, int32_t *path_out, float *score_out,
+                  flashv_report *report);
+/* FLASH-BS, calc() of S:548-577.  B = BeamSearchWidth (1 <= B <= K).  path entries may be -1. */
+int flashv_bs_decode(flashv_model *model, const int32_t *ob, int T, int N, int B, int32_t *path_out,
+                     float *score_out, flashv_report *report);
+/* `batch` independent sequences of one HMM: ob[batch][T] -> path_out[batch][T], score_out[batch]. */
+int flashv_decode_batch(flashv_model *model, const int32_t *ob, int batch, int T, int N, int32_t *path_out,
+                        float *score_out, flashv_report *report);
+int flashv_bs_decode_batch(flashv_model *model, const int32_t *ob, int batch, int T, int N, int B,
+                           int32_t *path_out, float *score_out, flashv_report *report);
+
+/* ---- staged decodes (what the one-call forms do; lets a caller keep inputs resident) ---- */
+/* B == 0 selects FLASH, B >= 1 FLASH-BS. */
+int flashv_plan_create(flashv_model *model, int T, int N, int batch, int B, int engine, flashv_plan **out);
+void flashv_plan_destroy(flashv_plan *plan);
+int flashv_plan_upload(flashv_plan *plan, const int32_t *ob);                 /* H2D, async on the ctx stream */
+int flashv_plan_run(flashv_plan *plan);                                       /* kernels only, async */
+int flashv_plan_download(flashv_plan *plan, int32_t *path_out, float *score_out); /* D2H + stream sync */
+int flashv_plan_report(flashv_plan *plan, flashv_report *report);            /* of the last run (syncs) */
+
+/* ---- pieces of the pass, exposed for per-step parity tests ---------------------------- */
+/* Start vector of nvviter / nvviterNdivide (F:142, F:220): prev_state < 0 selects the pi form. */
+int flashv_trellis_init(flashv_model *model, int prev_state, int ob0, float *delta_out);
+/* One max-plus step (F:165-174): delta_in[K], symbol o -> delta_out[K], psi_out[K] (-1 = dead). */
+int flashv_trellis_step(flashv_model *model, const float *delta_in, int o, float *delta_out, int32_t *psi_out,
+                        int engine);
+/* One FLASH-BS score step (S:437-446) and the heap rebuild (S:167-211). */
+int flashv_bs_score_step(flashv_model *model, const float *heap_val, const int32_t *heap_state, int B, int o,
+                         float *score_out, int32_t *arg_slot_out);
+int flashv_bs_heap_replay(flashv_ctx *ctx, const float *score, int K, int B, float *heap_val_out,
+                          int32_t *heap_state_out);
+
+/* ---- host-side pure functions ---------------------------------------------------------- */
+/* The FIFO task list of F:284-304 / F:349-359: returns the task count, fills L[], R[] (capacity
+ * T), *first_pass and mids[N-1] (may be NULL). */
+int flashv_task_list(int T, int N, int *L, int *R, int *first_pass, int *mids);
+long long flashv_executed_steps(int T, int N);
+int flashv_memory_bytes(int K, int T, int N);    /* F:355, F:364-367 */
+int flashv_bs_memory_bytes(int T, int N, int B); /* S:564, S:573-576 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

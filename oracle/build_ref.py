@@ -88,14 +88,14 @@ def data_file(data_dir: Path, kind, K, T, prob) -> Path:
 
 
 # What bench.py (cpu_baseline / --impl reference) and smoke() look for on the GPU box.
-# K=3965 at T=32 is the bounded sample of the headline workload: the full T=256 run takes
+# K=3965 at T=34 is the bounded sample of the headline workload: the full T=256 run takes
 # ~173 s on 8 cores.
 STANDARD = [
     ("FLASH", 64, 50, 256, 0.253, 8, None),
     ("FLASH_BS", 64, 50, 256, 0.253, 8, 8),
-    ("FLASH", 3965, 50, 32, 0.112, 8, None),
-    ("FLASH", 3965, 50, 32, 0.112, 16, None),
-    ("FLASH_BS", 3965, 50, 32, 0.112, 8, 128),
+    ("FLASH", 3965, 50, 34, 0.112, 8, None),
+    ("FLASH", 3965, 50, 34, 0.112, 16, None),
+    ("FLASH_BS", 3965, 50, 34, 0.112, 8, 128),
     ("FLASH_BS", 3965, 50, 256, 0.112, 8, 128),
 ]
 

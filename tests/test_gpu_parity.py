@@ -1,0 +1,241 @@
+"""Parity of the CUDA path (through the C ABI of libflashv.so) against the oracle and against
+the reference's own outputs.  Bit-exact: paths are integer arrays, scores are compared as float32
+bit patterns."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NAMES, golden_cases, load_golden, random_hmm
+
+pytestmark = pytest.mark.gpu
+
+NEG_MAX = np.float32(-3.4028234663852886e38)
+
+
+def _bits(x):
+    return np.asarray(x, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def golden_models(fv, gpu_ctx):
+    out = {}
+    for name in GOLDEN_NAMES:
+        g = load_golden(name)
+        out[name] = fv.Model(gpu_ctx, g["A"], g["B"], g["Pi"])
+    yield out
+    for m in out.values():
+        m.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_reference_golden_vectors(fv, oracle_mod, golden_models, name):
+    """Same HMM + observations the unmodified reference binaries decoded: same path, same memory line."""
+    g = load_golden(name)
+    model = golden_models[name]
+    om = oracle_mod.OracleModel(g["A"], g["B"], g["Pi"])
+    for case in golden_cases(name):
+        if case["prog"] == 0:
+            path, score, rep = model.decode(case["ob"], case["N"])
+            _, oscore, _ = om.flash(case["ob"], case["N"])
+        else:
+            path, score, rep = model.bs_decode(case["ob"], case["N"], case["B"])
+            _, oscore, _ = om.flash_bs(case["ob"], case["N"], case["B"])
+        assert np.array_equal(path, case["path"]), (name, case["prog"], case["N"], case["B"])
+        assert rep.memory_bytes == case["memory"]
+        assert _bits(score) == _bits(oscore), (name, case["prog"], case["N"], case["B"])
+
+
+@pytest.mark.parametrize("engine", ["STEP", "PERSISTENT"])
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_both_engines_on_goldens(fv, golden_models, name, engine):
+    eng = getattr(fv, "ENGINE_" + engine)
+    model = golden_models[name]
+    for case in golden_cases(name):
+        if case["prog"] != 0:
+            continue
+        plan = fv.Plan(model, len(case["ob"]), case["N"], 1, 0, eng)
+        plan.upload(case["ob"])
+        plan.run()
+        paths, _ = plan.download()
+        assert plan.report().engine == eng
+        plan.close()
+        assert np.array_equal(paths[0], case["path"]), (name, engine, case["N"])
+
+
+@pytest.mark.parametrize("engine", ["STEP", "PERSISTENT"])
+@pytest.mark.parametrize("K,M,p,seed", [(5, 3, 0.9, 1), (129, 7, 0.3, 2), (300, 50, 0.1, 3), (1000, 50, 0.05, 4),
+                                        (1500, 11, 0.2, 5), (2049, 5, 0.02, 6), (4100, 4, 0.01, 7)])
+def test_trellis_step_bit_exact(fv, oracle_mod, gpu_ctx, K, M, p, seed, engine):
+    """delta_t and psi_t of single steps (F:165-174), incl. -inf starts, ties and dead columns."""
+    eng = getattr(fv, "ENGINE_" + engine)
+    A, B, Pi = random_hmm(K, M, p, seed)
+    if seed % 2:
+        A[:, : K // 3] = A[:, [0]]  # repeated columns -> exact ties between predecessors
+    om = oracle_mod.OracleModel(A, B, Pi)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    rng = np.random.RandomState(seed)
+    d = om.init(-1, 0)
+    assert _bits(model.trellis_init(-1, 0)).tolist() == _bits(d).tolist()
+    s = int(rng.randint(K))
+    assert _bits(model.trellis_init(s, M - 1)).tolist() == _bits(om.init(s, M - 1)).tolist()
+    d = om.init(s, M - 1)  # holds -inf where A[s][i] == 0
+    for it in range(6):
+        o = int(rng.randint(M))
+        want_d, want_psi = om.step(d, o)
+        got_d, got_psi = model.trellis_step(d, o, eng)
+        assert np.array_equal(got_psi, want_psi), (it, np.nonzero(got_psi != want_psi)[0][:5])
+        assert np.array_equal(_bits(got_d), _bits(want_d)), it
+        d = want_d
+        if it == 3:  # scale far away from zero: coarser float grid, many more near-ties
+            d = (d * np.float32(37.0)).astype(np.float32)
+    # a vector that is dead almost everywhere
+    d = np.full(K, NEG_MAX, np.float32)
+    d[rng.randint(K)] = np.float32(-12.5)
+    want_d, want_psi = om.step(d, 0)
+    got_d, got_psi = model.trellis_step(d, 0, eng)
+    assert np.array_equal(got_psi, want_psi) and np.array_equal(_bits(got_d), _bits(want_d))
+    model.close()
+
+
+@pytest.mark.parametrize("K,M,T,p,seed", [(5, 3, 9, 0.9, 11), (97, 6, 33, 0.3, 12), (300, 50, 64, 0.1, 13),
+                                          (640, 20, 40, 0.05, 14), (1111, 9, 25, 0.3, 15)])
+def test_flash_random_models_vs_oracle(fv, oracle_mod, gpu_ctx, K, M, T, p, seed):
+    A, B, Pi = random_hmm(K, M, p, seed)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    rng = np.random.RandomState(seed)
+    ob = rng.randint(0, M, T).astype(np.int32)
+    for N in (1, 2, 3, 4, 7, T // 2 - 1, T // 2 + 1, T):
+        if N < 1 or (N > 2 and T == 2 * N):
+            continue
+        want, wscore, wmem = om.flash(ob, N)
+        if not wscore > NEG_MAX:
+            continue  # every path dead: the reference reads uninitialised trackers there
+        for eng in (fv.ENGINE_STEP, fv.ENGINE_PERSISTENT):
+            plan = fv.Plan(model, T, N, 1, 0, eng)
+            plan.upload(ob)
+            plan.run()
+            paths, scores = plan.download()
+            plan.close()
+            assert np.array_equal(paths[0], want), (N, eng)
+            assert _bits(scores[0]) == _bits(wscore)
+    model.close()
+
+
+@pytest.mark.parametrize("K,M,T,p,seed", [(8, 3, 12, 0.9, 21), (97, 6, 33, 0.3, 22), (300, 50, 64, 0.1, 23),
+                                          (700, 20, 30, 0.05, 24)])
+def test_flash_bs_random_models_vs_oracle(fv, oracle_mod, gpu_ctx, K, M, T, p, seed):
+    A, B, Pi = random_hmm(K, M, p, seed)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    rng = np.random.RandomState(seed)
+    ob = rng.randint(0, M, T).astype(np.int32)
+    for N in (1, 2, 3, 5, T // 2 - 1):
+        for Bw in (1, 2, 3, 7, 32, K // 2, K):
+            if N < 1 or Bw > K or (N > 2 and T == 2 * N):
+                continue
+            want, wscore, wmem = om.flash_bs(ob, N, Bw)
+            got, score, rep = model.bs_decode(ob, N, Bw)
+            assert np.array_equal(got, want), (N, Bw, np.nonzero(got != want)[0][:8])
+            assert _bits(score) == _bits(wscore) and rep.memory_bytes == wmem
+    model.close()
+
+
+def test_bs_pieces_bit_exact(fv, oracle_mod, gpu_ctx):
+    """Score step (S:437-446) and heap rebuild (S:167-211) on their own, incl. heavy ties."""
+    K, M = 777, 9
+    A, B, Pi = random_hmm(K, M, 0.2, 31)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    rng = np.random.RandomState(31)
+    for Bw in (1, 2, 5, 64, 128, 777):
+        score = np.float32(-rng.uniform(0, 30, K))
+        if Bw % 2 == 0:
+            score = np.round(score)  # many equal values: tie rules of S:114, S:152, S:193
+        pay = np.arange(K, dtype=np.int32)
+        hv, hs, _ = oracle_mod.heap_replay(score, pay, Bw)
+        ghv, ghs = gpu_ctx.heap_replay(score, Bw)
+        assert np.array_equal(ghs, hs) and np.array_equal(_bits(ghv), _bits(hv)), Bw
+        wscore, warg = om.bs_score_step(hv, hs, 3)
+        gscore, garg = model.bs_score_step(hv, hs, 3)
+        assert np.array_equal(garg, warg) and np.array_equal(_bits(gscore), _bits(wscore)), Bw
+    model.close()
+
+
+def test_batch_equals_single(fv, oracle_mod, gpu_ctx):
+    K, M, T = 200, 12, 48
+    A, B, Pi = random_hmm(K, M, 0.15, 41)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    rng = np.random.RandomState(41)
+    obs = rng.randint(0, M, (7, T)).astype(np.int32)
+    for N in (1, 4, 9):
+        paths, scores, rep = model.decode_batch(obs, N)
+        for b in range(obs.shape[0]):
+            want, wscore, _ = om.flash(obs[b], N)
+            assert np.array_equal(paths[b], want), (N, b)
+            assert _bits(scores[b]) == _bits(wscore)
+    paths, scores, rep = model.decode_batch(obs, 4, B=16)
+    for b in range(obs.shape[0]):
+        want, wscore, _ = om.flash_bs(obs[b], 4, 16)
+        assert np.array_equal(paths[b], want) and _bits(scores[b]) == _bits(wscore)
+    model.close()
+
+
+def test_error_behaviour(fv, gpu_ctx):
+    A, B, Pi = random_hmm(16, 4, 0.5, 51)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    ob = np.zeros(16, np.int32)
+    with pytest.raises(fv.FlashvError) as e:
+        model.decode(ob, 8)  # T == 2N
+    assert e.value.code == fv.ERR_ARG
+    with pytest.raises(fv.FlashvError):
+        model.bs_decode(ob, 2, 17)  # B > K
+    with pytest.raises(fv.FlashvError):
+        model.decode(np.full(16, 4, np.int32), 2)  # symbol outside [0,M)
+    with pytest.raises(fv.FlashvError):
+        model.decode(ob[:1], 1)  # T < 2
+    bad = A.copy()
+    bad[0, 0] = 1.5
+    with pytest.raises(fv.FlashvError) as e:
+        fv.Model(gpu_ctx, bad, B, Pi)
+    assert e.value.code == fv.ERR_DOMAIN
+    model.close()
+
+
+@pytest.fixture(scope="module")
+def headline(fv, oracle_mod, gpu_ctx):
+    """BASELINE.json configs[1]/[2]: K=3965, M=50, T=256, p=0.112."""
+    K, M, T = 3965, 50, 256
+    A, B, Pi = random_hmm(K, M, 0.112, 1)
+    ob = np.random.RandomState(1).randint(0, M, T).astype(np.int32)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    yield model, om, ob, A
+    model.close()
+
+
+def test_headline_flash_vs_oracle(fv, headline):
+    model, om, ob, A = headline
+    for N in (64, 8):
+        want, wscore, wmem = om.flash(ob, N)
+        for eng in (fv.ENGINE_PERSISTENT, fv.ENGINE_STEP):
+            plan = fv.Plan(model, len(ob), N, 1, 0, eng)
+            plan.upload(ob)
+            plan.run()
+            paths, scores = plan.download()
+            rep = plan.report()
+            plan.close()
+            assert np.array_equal(paths[0], want), (N, eng)
+            assert _bits(scores[0]) == _bits(wscore)
+            assert rep.memory_bytes == wmem
+    # size-independent property: the decoded path only uses transitions that exist
+    assert (A[want[:-1], want[1:]] > 0).all()
+
+
+def test_headline_flash_bs_vs_oracle(fv, headline):
+    model, om, ob, A = headline
+    for N, Bw in ((8, 128), (8, 32), (1, 128)):
+        want, wscore, wmem = om.flash_bs(ob, N, Bw)
+        got, score, rep = model.bs_decode(ob, N, Bw)
+        assert np.array_equal(got, want), (N, Bw)
+        assert _bits(score) == _bits(wscore) and rep.memory_bytes == wmem

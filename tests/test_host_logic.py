@@ -1,0 +1,132 @@
+"""Host-side logic of libflashv.so that needs no GPU: the task tree, the reference's memory
+formulas, the text loader, and the arithmetic claim the trellis kernels rest on."""
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+@pytest.mark.parametrize("T,N", [(256, 1), (256, 2), (256, 3), (256, 8), (256, 64), (256, 127), (61, 30), (61, 31),
+                                 (100, 49), (40, 19), (2, 1), (3, 1), (5, 2), (7, 3), (1024, 256), (4096, 1024)])
+def test_task_list_matches_oracle(fv, oracle_mod, T, N):
+    tasks, fp, mids = fv.task_list(T, N)
+    otasks, ofp, omids = oracle_mod.task_list(T, N)
+    assert fp == ofp and mids == omids
+    assert tasks == otasks  # same FIFO order as the reference's queue (F:284-304)
+    assert len(tasks) == (T - N if fp else T - 1)
+    assert fv.executed_steps(T, N) == oracle_mod.executed_steps(T, N)
+    # every time index is decided exactly once: N-way pass (N entries) + one per task
+    decided = ([T - 1] + mids) if fp else [T - 1]
+    decided += [(l + r) >> 1 for l, r in tasks]
+    assert sorted(decided) == list(range(T))
+
+
+def test_task_list_rejects_broken_domain(fv):
+    for T, N in [(1, 1), (60, 30), (16, 8), (10, 0)]:
+        with pytest.raises(fv.FlashvError):
+            fv.task_list(T, N)
+
+
+def test_memory_formulas_match_reference(fv, oracle_mod):
+    for K, T, N in [(64, 256, 1), (64, 256, 8), (64, 256, 30), (3965, 256, 8), (512, 1024, 256), (37, 61, 31)]:
+        assert fv.memory_bytes(K, T, N) == oracle_mod.flash_memory_bytes(K, T, N)
+    for T, N, B in [(256, 8, 8), (256, 4, 32), (256, 8, 128), (256, 1, 128), (61, 30, 6)]:
+        assert fv.bs_memory_bytes(T, N, B) == oracle_mod.bs_memory_bytes(T, N, B)
+    assert fv.memory_bytes(64, 256, 8) == 8368 and fv.bs_memory_bytes(256, 8, 128) == 24944
+
+
+def test_text_loader_is_fscanf_compatible(fv, oracle_mod, tmp_path):
+    rng = np.random.RandomState(7)
+    vals = np.concatenate([rng.uniform(0, 1, 3996), [0.0, 1.0, 1e-17, 0.5, 0.1, 2.0 ** -24 + 2.0 ** -49]])
+    p = tmp_path / "A.txt"
+    np.savetxt(p, vals.reshape(-1, 6), fmt="%.16f")
+    a = fv.read_floats_text(p, vals.size)
+    b = oracle_mod.read_floats(p, vals.size)  # literal fscanf("%f"), F:85-91
+    assert a.tobytes() == b.tobytes()
+    q = tmp_path / "ob.txt"
+    ints = rng.randint(0, 50, 300)
+    np.savetxt(q, ints, fmt="%d", newline=" ")
+    assert np.array_equal(fv.read_ints_text(q, 300), oracle_mod.read_ints(q, 300))
+    with pytest.raises(IOError):
+        fv.read_floats_text(p, vals.size + 5)
+
+
+def _ord(x):
+    b = x.view(np.int32).astype(np.int64)
+    return np.where(b >= 0, b, -(b & 0x7FFFFFFF))
+
+
+def test_window_filter_bound():
+    """The float estimate (tmp+d)+(float)logA is within 2 float steps of the reference's
+    (float)((double)(tmp+d)+logA) when all three operands are <= 0, so a 4-step window around the
+    largest estimate contains the exact first-argmax (trellis_common.cuh)."""
+    rng = np.random.RandomState(11)
+    worst = 0
+    for scale in (1.0, 30.0, 3000.0, 2.0e4):
+        n = 400000
+        tmp = np.float32(-rng.uniform(0.5, 6, n))
+        d = np.float32(-rng.uniform(0, scale, n))
+        la = np.log(rng.uniform(1e-6, 1.0, n).astype(np.float32).astype(np.float64))
+        pre = (tmp + d).astype(np.float32)
+        exact = (pre.astype(np.float64) + la).astype(np.float32)
+        est = (pre + la.astype(np.float32)).astype(np.float32)
+        worst = max(worst, int(np.abs(_ord(exact) - _ord(est)).max()))
+    assert worst <= 2
+    # columns: filtered first-argmax == exact first-argmax, also with ties and -inf entries
+    for trial in range(300):
+        K = 257
+        tmp = np.float32(-rng.uniform(0.5, 6))
+        d = np.float32(-rng.uniform(0, 50, K)) * np.float32(rng.choice([1, 40, 400]))
+        A = rng.uniform(0.01, 1, K) * (rng.uniform(0, 1, K) < 0.4)
+        A = (A / max(A.sum(), 1e-9)).astype(np.float32)
+        if trial % 3 == 0:
+            A[rng.randint(0, K, 40)] = A[rng.randint(0, K)]  # force repeated values
+        with np.errstate(divide="ignore"):
+            la = np.log(A.astype(np.float64))
+        pre = (tmp + d).astype(np.float32)
+        exact = (pre.astype(np.float64) + la).astype(np.float32)
+        est = (pre + la.astype(np.float32)).astype(np.float32)
+        best, arg = np.float32(-3.4028234663852886e38), -1
+        for k in range(K):
+            if exact[k] > best:
+                best, arg = exact[k], k
+        top = est.max()
+        if not top > np.float32(-3.4028234663852886e38):
+            assert arg == -1
+            continue
+        cand = np.nonzero(_ord(est) >= _ord(np.array([top], np.float32))[0] - 4)[0]
+        fb, fa = np.float32(-3.4028234663852886e38), -1
+        for k in cand:
+            if exact[k] > fb:
+                fb, fa = exact[k], int(k)
+        assert (fb, fa) == (best, arg)
+
+
+def test_header_declares_only_exported_symbols(fv):
+    text = (ROOT / "include" / "flashv.h").read_text()
+    declared = sorted(set(re.findall(r"\b(flashv_[a-z_A-Z0-9]+)\s*\(", text)))
+    assert declared == sorted(fv.ABI_SYMBOLS)
+    lib = fv.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_no_cpu_fallback_without_gpu(fv):
+    import ctypes as C
+
+    h = C.c_void_p()
+    rc = fv.lib().flashv_ctx_create(0, None, C.byref(h))
+    if rc == 0:  # a GPU is present: nothing to check here
+        fv.lib().flashv_ctx_destroy(h)
+        return
+    assert rc == fv.ERR_CUDA and b"no CPU path" in fv.lib().flashv_last_error()
+
+
+def test_product_never_touches_the_oracle():
+    pkg = ROOT / "flash-viterbi_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.c")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cpp")) + \
+            list(pkg.rglob("*.h")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("Makefile")):
+        t = f.read_text()
+        assert "flashv_oracle" not in t and "from oracle" not in t and "import oracle" not in t, f
