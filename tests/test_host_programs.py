@@ -1,0 +1,79 @@
+"""The reference-shaped host programs (flash-viterbi_b200/host/*.c) and their run.py driver."""
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+HOST = ROOT / "flash-viterbi_b200" / "host"
+sys.path.insert(0, str(HOST))
+
+P64 = {"K_STATE": 64, "T_STATE": 50, "obserRouteLEN": 256, "prob": 0.253, "MAX_THREADS": 8, "BeamSearchWidth": 8}
+
+
+def _write_k64_text(tmp_path):
+    import gen_hmm
+
+    A, B, Pi = gen_hmm.make_hmm(64, 50, 0.253, 1)  # same numbers as data_script.py -s 1
+    g = load_golden("hmm_k64")
+    assert np.array_equal(gen_hmm.as_reference_floats(A), g["A"])
+    gen_hmm.write_text(tmp_path / "data", 64, 256, 0.253, A, B, Pi, g["obs"][0])
+    return g
+
+
+def test_run_py_substitution_hits_every_knob(fv):
+    """src/run.py's regexes (R:29-47) must all match our host sources, and the result must compile."""
+    import run as host_run
+
+    for program in host_run.PROGRAMS:
+        src = (HOST / f"{program}.c").read_text()
+        p = {"K_STATE": 3965, "T_STATE": 50, "obserRouteLEN": 256, "prob": 0.112, "MAX_THREADS": 1, "BeamSearchWidth": 32}
+        out = host_run.substitute(src, p, "./somewhere/", program)
+        assert "#define K_STATE 3965" in out and "#define MAX_THREADS 1" in out and 'data_path[] = "./somewhere/"' in out
+        assert "prob%.3f" in out and "const float prob = 0.112;" in out
+        if "BS" in program:
+            assert "const int BeamSearchWidth = 32;" in out
+    # the three report lines keep the reference's printf shapes (F:378, F:119-123)
+    src = (HOST / "FLASH_Viterbi_multithread.c").read_text()
+    for shape in ('"time: %lf \\n"', '"path: ["', '"%d "', '"memory: %d\\n"'):
+        assert shape in src
+
+
+def test_host_programs_compile(fv, tmp_path):
+    import run as host_run
+
+    for program in host_run.PROGRAMS:
+        binary = host_run.compile_program(program, P64, "./data/", tmp_path)
+        assert binary.exists()
+
+
+@pytest.mark.gpu
+def test_host_program_matches_reference_binary(fv, tmp_path):
+    """Our program and the UNMODIFIED reference binary on the same text files: byte-identical
+    path: and memory: lines (the reference binaries are prebuilt into oracle/_ref/)."""
+    import run as host_run
+    from oracle import build_ref
+
+    g = _write_k64_text(tmp_path)
+    for program, prog, B in (("FLASH_Viterbi_multithread", "FLASH", None), ("FLASH_BS_Viterbi_multithread", "FLASH_BS", 8)):
+        binary = host_run.compile_program(program, P64, "./data/", tmp_path / "build")
+        ours = subprocess.run([str(binary)], cwd=tmp_path, capture_output=True, text=True)
+        assert ours.returncode == 0, ours.stderr
+        assert re.search(r"time: ([\d.]+)", ours.stdout) and re.search(r"memory: (\d+)", ours.stdout)  # R:75-76
+        ref_bin = build_ref.OUT_DIR / build_ref.binary_name(prog, 64, 50, 256, 0.253, 8, B)
+        if not ref_bin.exists():
+            if not build_ref.reference_available():
+                pytest.skip("reference binary not prebuilt")
+            ref_bin = build_ref.build(prog, 64, 50, 256, 0.253, 8, B)
+        ref = subprocess.run([str(ref_bin)], cwd=tmp_path, capture_output=True, text=True)
+        assert ref.returncode == 0
+        pick = lambda out, key: [ln for ln in out.splitlines() if ln.startswith(key)][0]
+        assert pick(ours.stdout, "path:") == pick(ref.stdout, "path:")
+        assert pick(ours.stdout, "memory:") == pick(ref.stdout, "memory:")
+        # and the golden vector recorded at build time says the same
+        row = [c for c in range(len(g["case_prog"])) if g["case_prog"][c] == (0 if B is None else 1)
+               and g["case_seq"][c] == 0 and g["case_N"][c] == 8 and g["case_B"][c] == (B or 0)][0]
+        assert pick(ours.stdout, "path:") == "path: [" + "".join(f"{x} " for x in g["case_path"][row]) + "]"
