@@ -31,11 +31,14 @@ __global__ void k_flash_init(const VecDesc *__restrict__ vecs, int nvec, const i
 }
 
 // ---- engine STEP: one launch per trellis step ------------------------------------------------
-// grid.x: blocks of 8 destination columns (one per warp); grid.y: groups of QB vectors.
-// A warp owns column i: lane l reads hiT[i][4*(l+32u) .. +3] as one 128-bit load per u, so the
-// warp streams the column as contiguous 512-byte requests; delta of the group's vectors sits in
-// shared memory.  Per update: FADD, FADD, FMNMX (estimate only); the exact value is recovered by
-// resolve_column() for the handful of candidates inside the window.
+// A block of NWARP warps keeps delta of QB vectors in shared memory and walks over tiles of
+// NWARP*RI destination columns (grid.x workers per vector group, grid.y vector groups).  A warp
+// owns RI columns of the tile: lane l reads hiT[i][4*(l+32u) .. +3] as one 128-bit load per u, so
+// a column streams as contiguous 512-byte requests straight from L2/HBM into registers, and every
+// hi value meets QB delta vectors, every delta value RI columns (an RI x QB register tile of
+// running maxima per lane and float4 component).  Per update: FADD, FADD, FMNMX (estimate only);
+// the exact value is recovered by resolve_column() for the handful of candidates inside the
+// window.  (QB,RI,NWARP) = (1,1,8) for single vectors, (8,2,16) for the batched tree levels.
 struct StepArgs {
     const float *hiT;
     const double *LAd;
@@ -51,10 +54,11 @@ struct StepArgs {
     int psi16;
 };
 
-template <int QB>
-__global__ void __launch_bounds__(256) k_flash_step(const StepArgs a)
+template <int QB, int RI, int NWARP>
+__global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
 {
     extern __shared__ float4 sdelta4[];
+    constexpr int NT = NWARP * 32;
     const int Kp4 = a.Kp >> 2;
     const int v0 = blockIdx.y * QB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -62,51 +66,75 @@ __global__ void __launch_bounds__(256) k_flash_step(const StepArgs a)
     for (int q = 0; q < QB; ++q) {
         const bool live = v0 + q < a.nact;
         const float4 *src = reinterpret_cast<const float4 *>(a.din + (size_t)(v0 + q) * a.Kp);
-        for (int t = tid; t < Kp4; t += 256) sdelta4[q * Kp4 + t] = live ? src[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = tid; t < Kp4; t += NT) sdelta4[q * Kp4 + t] = live ? src[t] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    const int i = blockIdx.x * 8 + warp;
-    if (i >= a.K) return;
+    const float *sdelta = reinterpret_cast<const float *>(sdelta4);
 
-    float tmp[QB];
     int jj[QB];
+    const float *tmp_row[QB];
 #pragma unroll
     for (int q = 0; q < QB; ++q) {
-        tmp[q] = 0.f, jj[q] = 0;
+        jj[q] = 0, tmp_row[q] = a.LBf;
         if (v0 + q < a.nact) {
             const VecDesc vd = a.vecs[v0 + q];
             jj[q] = vd.L + a.s;
-            tmp[q] = __ldg(a.LBf + (size_t)a.ob[(size_t)vd.seq * a.T + jj[q]] * a.Kp + i);  // F:167
+            tmp_row[q] = a.LBf + (size_t)a.ob[(size_t)vd.seq * a.T + jj[q]] * a.Kp;  // F:167
         }
     }
-    float cm[QB][4];
-#pragma unroll
-    for (int q = 0; q < QB; ++q) cm[q][0] = cm[q][1] = cm[q][2] = cm[q][3] = -INFINITY;
 
-    const float4 *col4 = reinterpret_cast<const float4 *>(a.hiT + (size_t)i * a.Kp);
-#pragma unroll 4
-    for (int t = lane; t < Kp4; t += 32) {
-        const float4 h = __ldg(col4 + t);
+    const int ntiles = (a.K + NWARP * RI - 1) / (NWARP * RI);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int ibase = (tile * NWARP + warp) * RI;
+        if (ibase >= a.K) continue;  // warp-uniform; no block-wide barrier below
+        int col_i[RI];
+        const float4 *col4[RI];
+        float tmp[RI][QB];
+        float cm[RI][QB][4];
 #pragma unroll
-        for (int q = 0; q < QB; ++q) {
-            const float4 d = sdelta4[q * Kp4 + t];
-            cm[q][0] = fmaxf(cm[q][0], __fadd_rn(__fadd_rn(tmp[q], d.x), h.x));
-            cm[q][1] = fmaxf(cm[q][1], __fadd_rn(__fadd_rn(tmp[q], d.y), h.y));
-            cm[q][2] = fmaxf(cm[q][2], __fadd_rn(__fadd_rn(tmp[q], d.z), h.z));
-            cm[q][3] = fmaxf(cm[q][3], __fadd_rn(__fadd_rn(tmp[q], d.w), h.w));
+        for (int r = 0; r < RI; ++r) {
+            col_i[r] = min(ibase + r, a.K - 1);  // a clamped duplicate column is computed and dropped
+            col4[r] = reinterpret_cast<const float4 *>(a.hiT + (size_t)col_i[r] * a.Kp);
+#pragma unroll
+            for (int q = 0; q < QB; ++q) {
+                tmp[r][q] = __ldg(tmp_row[q] + col_i[r]);
+                cm[r][q][0] = cm[r][q][1] = cm[r][q][2] = cm[r][q][3] = -INFINITY;
+            }
         }
-    }
-    const float *col = a.hiT + (size_t)i * a.Kp;
-    const float *sdelta = reinterpret_cast<const float *>(sdelta4);
+        constexpr int UNROLL = QB * RI >= 8 ? 2 : (QB * RI >= 2 ? 4 : 8);
+#pragma unroll UNROLL
+        for (int t = lane; t < Kp4; t += 32) {
+            float4 h[RI];
 #pragma unroll
-    for (int q = 0; q < QB; ++q) {
-        if (v0 + q >= a.nact) continue;  // warp-uniform
-        const Best b = resolve_column(cm[q], tmp[q], col, sdelta + (size_t)q * a.Kp, a.LAd, a.K, a.Kp, i, lane);
-        if (lane == 0) {
-            a.dout[(size_t)(v0 + q) * a.Kp + i] = b.x;
-            const VecDesc vd = a.vecs[v0 + q];
-            if (jj[q] >= vd.mid + 1)  // F:242: only steps from the latch on are ever read back
-                psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (jj[q] - vd.mid - 1)) * a.K + i, b.k);
+            for (int r = 0; r < RI; ++r) h[r] = __ldg(col4[r] + t);
+#pragma unroll
+            for (int q = 0; q < QB; ++q) {
+                const float4 d = sdelta4[q * Kp4 + t];
+#pragma unroll
+                for (int r = 0; r < RI; ++r) {
+                    cm[r][q][0] = fmaxf(cm[r][q][0], __fadd_rn(__fadd_rn(tmp[r][q], d.x), h[r].x));
+                    cm[r][q][1] = fmaxf(cm[r][q][1], __fadd_rn(__fadd_rn(tmp[r][q], d.y), h[r].y));
+                    cm[r][q][2] = fmaxf(cm[r][q][2], __fadd_rn(__fadd_rn(tmp[r][q], d.z), h[r].z));
+                    cm[r][q][3] = fmaxf(cm[r][q][3], __fadd_rn(__fadd_rn(tmp[r][q], d.w), h[r].w));
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+            if (ibase + r >= a.K) continue;  // warp-uniform
+            const int i = ibase + r;
+            const float *col = a.hiT + (size_t)i * a.Kp;
+#pragma unroll
+            for (int q = 0; q < QB; ++q) {
+                if (v0 + q >= a.nact) continue;  // warp-uniform
+                const Best b = resolve_column(cm[r][q], tmp[r][q], col, sdelta + (size_t)q * a.Kp, a.LAd, a.K, a.Kp, i, lane);
+                if (lane == 0) {
+                    a.dout[(size_t)(v0 + q) * a.Kp + i] = b.x;
+                    const VecDesc vd = a.vecs[v0 + q];
+                    if (jj[q] >= vd.mid + 1)  // F:242: only steps from the latch on are ever read back
+                        psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (jj[q] - vd.mid - 1)) * a.K + i, b.k);
+                }
+            }
         }
     }
 }
@@ -166,28 +194,37 @@ __global__ void k_flash_backtrack(const VecDesc *__restrict__ vecs, int nvec, co
 }
 
 // ---- host orchestration -------------------------------------------------------------------------
-template <int QB>
-static cudaError_t launch_step(const StepArgs &a, int nact, cudaStream_t st)
+template <int QB, int RI, int NWARP>
+static cudaError_t launch_step(const StepArgs &a, int nact, int sm_count, cudaStream_t st)
 {
     const size_t smem = (size_t)QB * a.Kp * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_flash_step<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e =
+            cudaFuncSetAttribute(k_flash_step<QB, RI, NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid((a.K + 7) / 8, (nact + QB - 1) / QB);
-    k_flash_step<QB><<<grid, 256, smem, st>>>(a);
+    const int ngroups = (nact + QB - 1) / QB;
+    const int ntiles = (a.K + NWARP * RI - 1) / (NWARP * RI);
+    // blocks that fit at once (shared memory bound), spread over the vector groups
+    int per_sm = smem ? (int)((200 * 1024) / smem) : 8;
+    per_sm = per_sm < 1 ? 1 : (per_sm > 2048 / (NWARP * 32) ? 2048 / (NWARP * 32) : per_sm);
+    int workers = (sm_count * per_sm + ngroups - 1) / ngroups;
+    if (workers > ntiles) workers = ntiles;
+    if (workers < 1) workers = 1;
+    dim3 grid(workers, ngroups);
+    k_flash_step<QB, RI, NWARP><<<grid, NWARP * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-static int pick_qb(int nact, int Kp)
+static cudaError_t dispatch_step(const StepArgs &a, int nact, int sm_count, cudaStream_t st)
 {
-    // delta of QB vectors must fit in shared memory next to a second resident CTA
-    int cap = (96 * 1024) / (Kp * 4);
-    int qb = 1;
-    while (qb * 2 <= 4 && qb * 2 <= cap && qb * 2 <= nact) qb *= 2;
-    return qb;
+    const size_t vec_bytes = (size_t)a.Kp * 4;
+    if (nact >= 5 && 8 * vec_bytes <= 200 * 1024) return launch_step<8, 2, 16>(a, nact, sm_count, st);
+    if (nact >= 3 && 4 * vec_bytes <= 200 * 1024) return launch_step<4, 2, 8>(a, nact, sm_count, st);
+    if (nact >= 2 && 2 * vec_bytes <= 200 * 1024) return launch_step<2, 1, 8>(a, nact, sm_count, st);
+    return launch_step<1, 1, 8>(a, nact, sm_count, st);
 }
 
 int persistent_pass(flashv_plan *p, const Pass &pass);  // flash_persistent.cu
@@ -220,13 +257,7 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
             a.vecs = vecs, a.nact = pass.nactive[s], a.s = s;
             a.din = (s & 1) ? d0 : d1, a.dout = (s & 1) ? d1 : d0;
             a.ob = p->d_ob, a.T = T, a.psi = p->d_psi, a.psi16 = p->psi16;
-            cudaError_t e;
-            switch (pick_qb(a.nact, Kp)) {
-                case 4: e = launch_step<4>(a, a.nact, st); break;
-                case 2: e = launch_step<2>(a, a.nact, st); break;
-                default: e = launch_step<1>(a, a.nact, st); break;
-            }
-            FV_CUDA(e);
+            FV_CUDA(dispatch_step(a, a.nact, ctx->sm_count, st));
             ++p->launches;
         }
         final_delta = (pass.max_steps & 1) ? d1 : d0;
@@ -265,7 +296,7 @@ int flash_single_step(flashv_model *m, const float *d_in_dev, int o, float *d_ou
     a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.vecs = dv, a.nact = 1, a.s = 1, a.din = d_in_dev, a.dout = d_out_dev;
     a.ob = dob, a.T = 2, a.psi = psi_dev, a.psi16 = 0;
-    FV_CUDA(launch_step<1>(a, 1, ctx->stream));
+    FV_CUDA((launch_step<1, 1, 8>(a, 1, ctx->sm_count, ctx->stream)));
     return FLASHV_OK;
 }
 

@@ -4,24 +4,31 @@
 //
 //   * Each CTA owns a contiguous range of destination columns of hiT (K/gridDim of them), i.e. one
 //     contiguous ~K*Kp*4/gridDim byte slab that it re-reads every step — from L2 when the table
-//     fits (62.9 MB at K=3965 against 126 MB of L2).
-//   * Warp NW is the producer: one lane streams the slab through an NSTAGE-deep shared-memory ring
+//     fits (62.9 MB at K=3965 against 126 MB of L2; ncu: 97.7 % L2 hit rate, 0.25 % DRAM).
+//   * Warp NCW is the producer: one lane streams the slab through an NSTAGE-deep shared-memory ring
 //     with bulk TMA copies (cp.async.bulk ... mbarrier::complete_tx), running ahead across step
-//     boundaries since the table does not change.
-//   * Warps 0..NW-1 are consumers: a warp takes one column at a time; lane l owns k = 4*(l+32u)+c,
-//     keeps four running maxima of the float estimate (FADD, FADD, FMNMX per update), then the
-//     warp resolves the exact (value, first index) from the double table for the few candidates
-//     inside the window (trellis_common.cuh).  delta lives in registers when Kp <= 4096.
+//     boundaries since the table does not change — the ring refills while the CTAs sit in the grid
+//     barrier and reload delta.
+//   * Warps 0..NCW-1 are consumers.  A warp takes CPW columns at a time so one delta load from
+//     shared memory feeds CPW columns; lane l owns k = 4*(l+32u)+c and keeps four running maxima
+//     per column of the float estimate (FADD, FADD, FMNMX per update).  The exact (value, first
+//     index) comes from the double table for the few candidates inside the window
+//     (trellis_common.cuh): the candidates are found by re-scanning the winning chain in the
+//     shared-memory stage, their double loads are issued for all CPW columns before any is
+//     consumed, so a warp pays one HBM round trip per step.
 //   * Steps are separated by a grid-wide barrier (release/acquire counter in global memory); the
 //     next delta is re-read from L2 with ld.global.cg.
 //   F: = /root/reference/src/FLASH_Viterbi_multithread.c
+#include <stdlib.h>
+
 #include "flashv_internal.h"
 #include "trellis_common.cuh"
 
 namespace flashv {
 
-constexpr int NW = 7;                 // consumer warps (7 + producer = 8 warps: 2 per SM sub-partition, up to 255 registers each)
-constexpr int NCONS = NW * 32;        // consumer threads
+constexpr int NCW = 14;               // consumer warps
+constexpr int CPW = 2;                // columns a consumer warp processes together
+constexpr int NCONS = NCW * 32;       // consumer threads
 constexpr int NTHREADS = NCONS + 32;  // + producer warp
 constexpr int MAX_STAGES = 16;
 
@@ -112,24 +119,83 @@ struct PersistArgs {
     int l2_hint;
 };
 
-// Grid-wide barrier for the consumer threads of all CTAs: `epoch` counts from 1.
+// Grid-wide barrier for the consumer threads of all CTAs; `epoch` counts from 1.  The CTA-level
+// barrier orders every consumer's delta/psi stores before thread 0's release-add, and thread 0's
+// acquire-load before every consumer's reads after the second CTA-level barrier (causality order
+// is transitive over bar.sync), so no separate fences are needed.
 __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned epoch, int ctid)
 {
     named_bar_sync(1, NCONS);
     if (ctid == 0) {
-        __threadfence();
         red_release_gpu(bar, 1u);
         const unsigned want = epoch * gridDim.x;
         for (uint32_t spins = 0; ld_acquire_gpu(bar) < want; ++spins)
             if (spins > (1u << 28)) __trap();
-        __threadfence();
     }
     named_bar_sync(1, NCONS);
 }
 
-// NF4 > 0: delta in registers (NF4 float4 per lane, Kp <= 128*NF4, one chunk per column).
-// NF4 == 0: delta read from shared memory, columns streamed in `chunk`-float pieces.
-template <int NF4>
+// Candidates of one column inside the window, gathered lane-locally: the newest candidate's double
+// load stays in flight (`la`), older ones of the same lane are folded into `acc` on arrival.
+struct Pending {
+    Best acc;
+    double la;
+    float pre;
+    int k;
+    bool has;
+};
+
+__device__ __forceinline__ void pending_push(Pending &p, float pre, int k, const double *__restrict__ la_ptr)
+{
+    if (p.has) {
+        const float x = exact_cand(p.pre, p.la);
+        if (x > -FLT_MAX) best_take(p.acc, x, p.k);
+    }
+    p.pre = pre, p.k = k, p.la = __ldg(la_ptr), p.has = true;
+}
+
+__device__ __forceinline__ Best pending_finish(Pending &p)
+{
+    if (p.has) {
+        const float x = exact_cand(p.pre, p.la);
+        if (x > -FLT_MAX) best_take(p.acc, x, p.k);
+    }
+    Best b = warp_best(p.acc);
+    if (!(b.x > -FLT_MAX)) b.x = -FLT_MAX, b.k = -1;
+    return b;
+}
+
+// Find the window candidates of column i (estimates from `col`, which may point into the
+// shared-memory stage or into hiT) and start their exact loads.
+__device__ __forceinline__ void scan_column(Pending &p, const float (&cm)[4], float tmp, const float *col,
+                                            const float *sdelta, const double *__restrict__ LAd, int K, int Kp, int i,
+                                            int lane)
+{
+    p.acc = Best{-FLT_MAX, 0x7fffffff};
+    p.has = false;
+    p.la = 0.0, p.pre = 0.f, p.k = 0;
+    const float top = warp_max(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
+    if (!(top > -FLT_MAX)) return;  // dead column (warp-uniform)
+    const int thr = ford(top) - WINDOW_STEPS;
+    const int chain_len = Kp >> 7;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned hit = __ballot_sync(FULL_MASK, ford(cm[c]) >= thr);
+        while (hit) {
+            const int w = __ffs(hit) - 1;
+            hit &= hit - 1;
+            for (int u = lane; u < chain_len; u += 32) {
+                const int k = 4 * (w + 32 * u) + c;
+                if (k < K) {
+                    const float pre = __fadd_rn(tmp, sdelta[k]);
+                    const float est = __fadd_rn(pre, col[k]);
+                    if (ford(est) >= thr) pending_push(p, pre, k, LAd + (size_t)k * K + i);
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -153,19 +219,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
     }
     __syncthreads();
 
-    if (warp == NW) {
+    if (warp == NCW) {
         // ---------------- producer: the slab of this CTA, once per step, through the ring --------
         if (lane == 0) {
             const uint64_t pol = policy_evict_last();
             const unsigned char *slab = reinterpret_cast<const unsigned char *>(a.hiT + (size_t)c0 * a.Kp);
+            // item order = the order consumers need them: step, column group (CPW columns that one
+            // warp processes together), chunk, column within the group — a warp only ever waits
+            // for CPW consecutive items, so any ring depth >= CPW is deadlock-free
             uint32_t item = 0;
             for (int s = 1; s <= a.nsteps; ++s)
-                for (int w = 0; w < ncols * nchunks; ++w, ++item) {
-                    const uint32_t st = item % (uint32_t)a.nstage, use = item / (uint32_t)a.nstage;
-                    if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
-                    mbar_expect_tx(&full[st], stage_bytes);
-                    bulk_g2s(ring + (size_t)st * stage_bytes, slab + (size_t)w * stage_bytes, stage_bytes, &full[st], pol,
-                             a.l2_hint != 0);
+                for (int g0 = 0; g0 < ncols; g0 += CPW) {
+                    const int gcols = min(CPW, ncols - g0);
+                    for (int ch = 0; ch < nchunks; ++ch)
+                        for (int c = 0; c < gcols; ++c, ++item) {
+                            const uint32_t st = item % (uint32_t)a.nstage, use = item / (uint32_t)a.nstage;
+                            if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
+                            mbar_expect_tx(&full[st], stage_bytes);
+                            bulk_g2s(ring + (size_t)st * stage_bytes,
+                                     slab + ((size_t)(g0 + c) * a.Kp + (size_t)ch * a.chunk) * sizeof(float), stage_bytes,
+                                     &full[st], pol, a.l2_hint != 0);
+                        }
                 }
         }
         return;
@@ -181,56 +255,78 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             const float4 *din4 = reinterpret_cast<const float4 *>(din);
             for (int t = tid; t < Kp4; t += NCONS) sdelta4[t] = __ldcg(din4 + t);
         }
-        named_bar_sync(1, NCONS);
-        float4 dreg[NF4 > 0 ? NF4 : 1];
-        if (NF4 > 0) {
-#pragma unroll
-            for (int u = 0; u < NF4; ++u)
-                dreg[u] = (lane + 32 * u) < Kp4 ? sdelta4[lane + 32 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         const float *tmp_row = a.LBf + (size_t)__ldg(a.ob + j) * a.Kp;  // F:167
         const bool keep = j >= a.mid + 1;                                // F:242
+        named_bar_sync(1, NCONS);
 
-        for (int n = warp; n < ncols; n += NW) {
-            const int i = c0 + n;
-            const float tmp = __ldg(tmp_row + i);
-            float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int n0 = warp * CPW; n0 < ncols; n0 += NCW * CPW) {
+            const bool two = n0 + 1 < ncols;
+            const int i0 = c0 + n0, i1 = two ? i0 + 1 : i0;
+            const float tmp0 = __ldg(tmp_row + i0), tmp1 = __ldg(tmp_row + i1);
+            float cm0[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            float cm1[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            const float *last0 = nullptr, *last1 = nullptr;
+            uint32_t st0 = 0, st1 = 0;
             for (int ch = 0; ch < nchunks; ++ch) {
-                const uint32_t item = (uint32_t)((s - 1) * ncols + n) * (uint32_t)nchunks + (uint32_t)ch;
-                const uint32_t st = item % (uint32_t)a.nstage, use = item / (uint32_t)a.nstage;
-                mbar_wait(&full[st], use & 1);
-                const float4 *st4 = reinterpret_cast<const float4 *>(ring + (size_t)st * stage_bytes);
-                if (NF4 > 0) {
-#pragma unroll
-                    for (int u = 0; u < NF4; ++u) {
-                        if (lane + 32 * u < chunk4) {
-                            const float4 h = st4[lane + 32 * u];
-                            const float4 d = dreg[u];
-                            cm[0] = fmaxf(cm[0], __fadd_rn(__fadd_rn(tmp, d.x), h.x));
-                            cm[1] = fmaxf(cm[1], __fadd_rn(__fadd_rn(tmp, d.y), h.y));
-                            cm[2] = fmaxf(cm[2], __fadd_rn(__fadd_rn(tmp, d.z), h.z));
-                            cm[3] = fmaxf(cm[3], __fadd_rn(__fadd_rn(tmp, d.w), h.w));
-                        }
-                    }
-                } else {
-                    const float4 *d4 = sdelta4 + (size_t)ch * chunk4;
+                // ring items are numbered in the producer's order: step, group, chunk, column in group
+                const uint32_t item0 = (uint32_t)((s - 1) * ncols + n0) * (uint32_t)nchunks + (uint32_t)ch * (two ? 2u : 1u);
+                const uint32_t item1 = item0 + 1u;
+                st0 = item0 % (uint32_t)a.nstage;
+                mbar_wait(&full[st0], (item0 / (uint32_t)a.nstage) & 1);
+                const float4 *p0 = reinterpret_cast<const float4 *>(ring + (size_t)st0 * stage_bytes);
+                const float4 *p1 = p0;
+                if (two) {
+                    st1 = item1 % (uint32_t)a.nstage;
+                    mbar_wait(&full[st1], (item1 / (uint32_t)a.nstage) & 1);
+                    p1 = reinterpret_cast<const float4 *>(ring + (size_t)st1 * stage_bytes);
+                }
+                const float4 *d4 = sdelta4 + (size_t)ch * chunk4;
 #pragma unroll 4
-                    for (int t = lane; t < chunk4; t += 32) {
-                        const float4 h = st4[t];
-                        const float4 d = d4[t];
-                        cm[0] = fmaxf(cm[0], __fadd_rn(__fadd_rn(tmp, d.x), h.x));
-                        cm[1] = fmaxf(cm[1], __fadd_rn(__fadd_rn(tmp, d.y), h.y));
-                        cm[2] = fmaxf(cm[2], __fadd_rn(__fadd_rn(tmp, d.z), h.z));
-                        cm[3] = fmaxf(cm[3], __fadd_rn(__fadd_rn(tmp, d.w), h.w));
+                for (int t = lane; t < chunk4; t += 32) {
+                    const float4 d = d4[t];
+                    const float4 h0 = p0[t];
+                    const float4 h1 = p1[t];
+                    cm0[0] = fmaxf(cm0[0], __fadd_rn(__fadd_rn(tmp0, d.x), h0.x));
+                    cm0[1] = fmaxf(cm0[1], __fadd_rn(__fadd_rn(tmp0, d.y), h0.y));
+                    cm0[2] = fmaxf(cm0[2], __fadd_rn(__fadd_rn(tmp0, d.z), h0.z));
+                    cm0[3] = fmaxf(cm0[3], __fadd_rn(__fadd_rn(tmp0, d.w), h0.w));
+                    cm1[0] = fmaxf(cm1[0], __fadd_rn(__fadd_rn(tmp1, d.x), h1.x));
+                    cm1[1] = fmaxf(cm1[1], __fadd_rn(__fadd_rn(tmp1, d.y), h1.y));
+                    cm1[2] = fmaxf(cm1[2], __fadd_rn(__fadd_rn(tmp1, d.z), h1.z));
+                    cm1[3] = fmaxf(cm1[3], __fadd_rn(__fadd_rn(tmp1, d.w), h1.w));
+                }
+                last0 = reinterpret_cast<const float *>(p0);
+                last1 = reinterpret_cast<const float *>(p1);
+                if (ch + 1 < nchunks) {  // multi-chunk columns re-scan from hiT, so stages can go now
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&empty[st0]);
+                        if (two) mbar_arrive(&empty[st1]);
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[st]);
             }
-            const Best r = resolve_column(cm, tmp, a.hiT + (size_t)i * a.Kp, sdelta, a.LAd, a.K, a.Kp, i, lane);
+            // candidates: from the stage when it still holds the whole column, else from hiT (L2)
+            const float *col0 = nchunks == 1 ? last0 : a.hiT + (size_t)i0 * a.Kp;
+            const float *col1 = nchunks == 1 ? last1 : a.hiT + (size_t)i1 * a.Kp;
+            Pending q0, q1;
+            scan_column(q0, cm0, tmp0, col0, sdelta, a.LAd, a.K, a.Kp, i0, lane);
+            if (two) scan_column(q1, cm1, tmp1, col1, sdelta, a.LAd, a.K, a.Kp, i1, lane);
+            __syncwarp();
             if (lane == 0) {
-                dout[i] = r.x;
-                if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i, r.k);
+                mbar_arrive(&empty[st0]);
+                if (two) mbar_arrive(&empty[st1]);
+            }
+            const Best r0 = pending_finish(q0);
+            if (lane == 0) {
+                dout[i0] = r0.x;
+                if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i0, r0.k);
+            }
+            if (two) {
+                const Best r1 = pending_finish(q1);
+                if (lane == 0) {
+                    dout[i1] = r1.x;
+                    if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i1, r1.k);
+                }
             }
         }
         grid_barrier(a.bar, (unsigned)s, tid);
@@ -243,30 +339,30 @@ static size_t persist_smem(int Kp, int chunk, int nstage)
     return 2 * MAX_STAGES * sizeof(uint64_t) + (size_t)Kp * 4 + (size_t)nstage * chunk * 4;
 }
 
+static int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 static int launch_persist(flashv_ctx *ctx, PersistArgs &a)
 {
     const int Kp = a.Kp;
-    const bool in_regs = Kp <= 4096;
-    a.chunk = in_regs ? Kp : 4096;
+    a.chunk = Kp <= 4096 ? Kp : 4096;
     while (Kp % a.chunk) a.chunk -= 128;  // Kp is a multiple of 128, so this ends at >= 128
     const size_t fixed = persist_smem(Kp, 0, 0);
-    int nstage = (int)(((size_t)ctx->smem_optin - fixed) / ((size_t)a.chunk * 4));
-    if (nstage > MAX_STAGES) nstage = MAX_STAGES;
-    if (nstage < 2) {
+    if (fixed + 2 * (size_t)a.chunk * 4 > (size_t)ctx->smem_optin) {
         set_error("persistent engine: K=%d does not fit shared memory (%d bytes)", a.K, ctx->smem_optin);
         return FLASHV_ERR_ARG;
     }
+    int nstage = (int)(((size_t)ctx->smem_optin - fixed) / ((size_t)a.chunk * 4));
+    if (nstage > MAX_STAGES) nstage = MAX_STAGES;
+    const int cap = env_int("FLASHV_STAGES", 0);
+    if (cap >= 2 && cap < nstage) nstage = cap;
     a.nstage = nstage;
+    a.l2_hint = env_int("FLASHV_L2_HINT", 1);
     const size_t smem = persist_smem(Kp, a.chunk, nstage);
-    const void *fn;
-    if (!in_regs)
-        fn = (const void *)k_flash_persist<0>;
-    else if (Kp <= 1024)
-        fn = (const void *)k_flash_persist<8>;
-    else if (Kp <= 2048)
-        fn = (const void *)k_flash_persist<16>;
-    else
-        fn = (const void *)k_flash_persist<32>;
+    const void *fn = (const void *)k_flash_persist;
     FV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     FV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NTHREADS, smem));
@@ -282,27 +378,16 @@ static int launch_persist(flashv_ctx *ctx, PersistArgs &a)
     return FLASHV_OK;
 }
 
-static int l2_hint_enabled()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("FLASHV_L2_HINT");
-        v = e ? atoi(e) : 1;
-    }
-    return v;
-}
-
 int persistent_pass(flashv_plan *p, const Pass &pass)
 {
     flashv_model *m = p->model;
     const VecDesc &vd = pass.first_vec;  // the pass has exactly one vector (batch == 1)
     PersistArgs a;
     a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
-    a.ob = p->d_ob;  // batch == 1 for single-vector passes of sequence 0
+    a.ob = p->d_ob;
     a.L = vd.L, a.nsteps = vd.R - vd.L, a.mid = vd.mid, a.psi_row = vd.psi_row;
     a.d0 = p->d_delta, a.d1 = p->d_delta + (size_t)p->max_vec * m->Kp;
     a.psi = p->d_psi, a.psi16 = p->psi16, a.bar = p->d_sync;
-    a.l2_hint = l2_hint_enabled();
     int rc = launch_persist(m->ctx, a);
     if (rc == FLASHV_OK) p->launches += 1;
     return rc;
@@ -321,7 +406,6 @@ int persistent_single_step(flashv_model *m, const float *d_in_dev, int o, float 
     a.d0 = const_cast<float *>(d_in_dev), a.d1 = d_out_dev;
     a.psi = psi_dev, a.psi16 = 0;
     a.bar = reinterpret_cast<unsigned *>(m->scratch_i + 32);
-    a.l2_hint = l2_hint_enabled();
     return launch_persist(ctx, a);
 }
 
