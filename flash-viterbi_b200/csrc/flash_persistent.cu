@@ -31,6 +31,7 @@ constexpr int CPW = 2;                // columns a consumer warp processes toget
 constexpr int NCONS = NCW * 32;       // consumer threads
 constexpr int NTHREADS = NCONS + 32;  // + producer warp
 constexpr int MAX_STAGES = 16;
+constexpr int CTRL_BYTES = 2 * MAX_STAGES * 8 + 128;  // full[], empty[], the producer's issue counter
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -60,11 +61,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// Every spin loop of this kernel is bounded in wall time: a protocol bug must end in a trap within
+// seconds, not hang the device.
+constexpr unsigned long long WATCHDOG_NS = 4000000000ull;
+__device__ __forceinline__ unsigned long long now_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void watchdog(uint32_t spins, unsigned long long &t0)
+{
+    if ((spins & 1023u) == 1023u) {
+        const unsigned long long t = now_ns();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > WATCHDOG_NS) __trap();
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    // try_wait suspends in hardware for a bounded time; the outer loop is the watchdog
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 26)) __trap();
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) watchdog(spins, t0);
 }
 __device__ __forceinline__ uint64_t policy_evict_last()
 {
@@ -129,8 +146,8 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned epoch, int 
     if (ctid == 0) {
         red_release_gpu(bar, 1u);
         const unsigned want = epoch * gridDim.x;
-        for (uint32_t spins = 0; ld_acquire_gpu(bar) < want; ++spins)
-            if (spins > (1u << 28)) __trap();
+        unsigned long long t0 = 0;
+        for (uint32_t spins = 0; ld_acquire_gpu(bar) < want; ++spins) watchdog(spins, t0);
     }
     named_bar_sync(1, NCONS);
 }
@@ -205,7 +222,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
     const uint32_t stage_bytes = (uint32_t)a.chunk * 4u;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *empty = full + MAX_STAGES;
-    float4 *sdelta4 = reinterpret_cast<float4 *>(smem_raw + 2 * MAX_STAGES * sizeof(uint64_t));
+    volatile uint32_t *issued = reinterpret_cast<volatile uint32_t *>(empty + MAX_STAGES);  // items the producer has started
+    float4 *sdelta4 = reinterpret_cast<float4 *>(smem_raw + CTRL_BYTES);
     unsigned char *ring = reinterpret_cast<unsigned char *>(sdelta4 + Kp4);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -215,6 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
 
     if (tid == 0) {
         for (int s = 0; s < a.nstage; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
+        *issued = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -239,6 +258,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                             bulk_g2s(ring + (size_t)st * stage_bytes,
                                      slab + ((size_t)(g0 + c) * a.Kp + (size_t)ch * a.chunk) * sizeof(float), stage_bytes,
                                      &full[st], pol, a.l2_hint != 0);
+                            *issued = item + 1;
                         }
                 }
         }
@@ -272,6 +292,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                 const uint32_t item0 = (uint32_t)((s - 1) * ncols + n0) * (uint32_t)nchunks + (uint32_t)ch * (two ? 2u : 1u);
                 const uint32_t item1 = item0 + 1u;
                 st0 = item0 % (uint32_t)a.nstage;
+                // A parity wait is only meaningful once the stage is in the phase of THIS use: with more
+                // columns demanded at once than ring stages, a warp can get here before the stage's
+                // previous use has even landed, and try_wait would then report the older phase as done.
+                // The producer starts item i only after use i-nstage of the stage was released, so
+                // "item started" implies the barrier is in the right phase.
+                {
+                    unsigned long long t0 = 0;
+                    for (uint32_t spins = 0; *issued <= item0 + (two ? 1u : 0u); ++spins) watchdog(spins, t0);
+                }
                 mbar_wait(&full[st0], (item0 / (uint32_t)a.nstage) & 1);
                 const float4 *p0 = reinterpret_cast<const float4 *>(ring + (size_t)st0 * stage_bytes);
                 const float4 *p1 = p0;
@@ -336,7 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
 // ---- host side ---------------------------------------------------------------------------------
 static size_t persist_smem(int Kp, int chunk, int nstage)
 {
-    return 2 * MAX_STAGES * sizeof(uint64_t) + (size_t)Kp * 4 + (size_t)nstage * chunk * 4;
+    return CTRL_BYTES + (size_t)Kp * 4 + (size_t)nstage * chunk * 4;
 }
 
 static int env_int(const char *name, int dflt)

@@ -63,7 +63,7 @@ def test_both_engines_on_goldens(fv, golden_models, name, engine):
 
 @pytest.mark.parametrize("engine", ["STEP", "PERSISTENT"])
 @pytest.mark.parametrize("K,M,p,seed", [(5, 3, 0.9, 1), (129, 7, 0.3, 2), (300, 50, 0.1, 3), (1000, 50, 0.05, 4),
-                                        (1500, 11, 0.2, 5), (2049, 5, 0.02, 6), (4100, 4, 0.01, 7)])
+                                        (1500, 11, 0.2, 5), (2049, 5, 0.02, 6), (3965, 5, 0.05, 8), (4100, 4, 0.01, 7)])
 def test_trellis_step_bit_exact(fv, oracle_mod, gpu_ctx, K, M, p, seed, engine):
     """delta_t and psi_t of single steps (F:165-174), incl. -inf starts, ties and dead columns."""
     eng = getattr(fv, "ENGINE_" + engine)
