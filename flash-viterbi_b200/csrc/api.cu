@@ -140,7 +140,7 @@ extern "C" void flashv_model_destroy(flashv_model *m)
     cudaStreamSynchronize(m->ctx->stream);
     for (flashv_plan *p : m->plan_cache) flashv_plan_destroy(p);
     cudaFree(m->hiT), cudaFree(m->LAd), cudaFree(m->LBf), cudaFree(m->LBd), cudaFree(m->LPi);
-    cudaFree(m->scratch_f), cudaFree(m->scratch_i);
+    cudaFree(m->scratch_f), cudaFree(m->scratch_i), cudaFree(m->scratch_x);
     delete m;
 }
 
@@ -216,7 +216,7 @@ extern "C" int flashv_plan_create(flashv_model *m, int T, int N, int batch, int 
     }
     const int K = m->K, Kp = m->Kp;
     const size_t psi_bytes = (size_t)max_rows * K * (p->psi16 ? 2 : 4);
-    const size_t delta_bytes = (size_t)2 * p->max_vec * Kp * sizeof(float);
+    const size_t delta_bytes = (size_t)(2 * p->max_vec + 4) * Kp * sizeof(float);  // two delta sets + the persistent engine's {value,step} exchange buffers
     std::vector<uint8_t> ismid((size_t)T, 0);
     for (int mid : p->sched.mids) ismid[mid] = 1;
 

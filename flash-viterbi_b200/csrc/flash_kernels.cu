@@ -210,7 +210,7 @@ static cudaError_t launch_step(const StepArgs &a, int nact, int sm_count, cudaSt
     // blocks that fit at once (shared memory bound), spread over the vector groups
     int per_sm = smem ? (int)((200 * 1024) / smem) : 8;
     per_sm = per_sm < 1 ? 1 : (per_sm > 2048 / (NWARP * 32) ? 2048 / (NWARP * 32) : per_sm);
-    int workers = (sm_count * per_sm + ngroups - 1) / ngroups;
+    int workers = (sm_count * per_sm) / ngroups;  // round down: one extra block would cost a whole second wave
     if (workers > ntiles) workers = ntiles;
     if (workers < 1) workers = 1;
     dim3 grid(workers, ngroups);
@@ -249,7 +249,7 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
     if (persistent) {
         int rc = persistent_pass(p, pass);
         if (rc != FLASHV_OK) return rc;
-        final_delta = (pass.max_steps & 1) ? d1 : d0;
+        final_delta = d1;  // the persistent kernel leaves the last delta there
     } else {
         for (int s = 1; s <= pass.max_steps; ++s) {
             StepArgs a;

@@ -16,8 +16,8 @@
 //     (trellis_common.cuh): the candidates are found by re-scanning the winning chain in the
 //     shared-memory stage, their double loads are issued for all CPW columns before any is
 //     consumed, so a warp pays one HBM round trip per step.
-//   * Steps are separated by a grid-wide barrier (release/acquire counter in global memory); the
-//     next delta is re-read from L2 with ld.global.cg.
+//   * Steps hand over through the delta vector itself (NaN-armed buffers polled from L2, see
+//     delta_wait_load): no grid barrier, no atomics.
 //   F: = /root/reference/src/FLASH_Viterbi_multithread.c
 #include <stdlib.h>
 
@@ -30,7 +30,7 @@ constexpr int NCW = 14;               // consumer warps
 constexpr int CPW = 2;                // columns a consumer warp processes together
 constexpr int NCONS = NCW * 32;       // consumer threads
 constexpr int NTHREADS = NCONS + 32;  // + producer warp
-constexpr int MAX_STAGES = 16;
+constexpr int MAX_STAGES = 64;
 constexpr int CTRL_BYTES = 2 * MAX_STAGES * 8 + 128;  // full[], empty[], the producer's issue counter
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -109,17 +109,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_release_gpu(unsigned *p, unsigned v)
-{
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 struct PersistArgs {
     const float *hiT;
     const double *LAd;
@@ -127,27 +116,69 @@ struct PersistArgs {
     int K, Kp;
     const int32_t *ob;  // observations of the sequence this vector walks
     int L, nsteps, mid, psi_row;
-    float *d0, *d1;  // step s reads (s odd ? d0 : d1) and writes the other
+    const float *d_init;      // delta of the start vector (plain floats, written by k_flash_init)
+    float *d_final;           // delta after the last step (plain floats, for k_flash_end)
+    unsigned long long *xch;  // [2][Kp] exchange buffers of {value, step} words, zeroed before the launch
     void *psi;
     int psi16;
-    unsigned *bar;  // zeroed before the launch
-    int chunk;      // floats per ring stage (multiple of 128, divides Kp)
+    int chunk;      // floats per ring stage (multiple of 128; the last chunk of a column may be shorter)
     int nstage;
     int l2_hint;
 };
 
-// Grid-wide barrier for the consumer threads of all CTAs; `epoch` counts from 1.  The CTA-level
-// barrier orders every consumer's delta/psi stores before thread 0's release-add, and thread 0's
-// acquire-load before every consumer's reads after the second CTA-level barrier (causality order
-// is transitive over bar.sync), so no separate fences are needed.
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned epoch, int ctid)
+// ---- step-to-step hand-over without a barrier ------------------------------------------------
+// The only data a step needs from the other CTAs is the previous delta vector, so the vector itself
+// carries the flag: every entry is published as ONE 64-bit store {float bits, step number} into
+// an exchange buffer, and every CTA polls the buffer of the previous step (ld.volatile, served by
+// L2) until all K entries show that step number, staging the values in shared memory as it goes.
+// A 64-bit store is single-copy atomic, so no fence, no atomic and no ordering between different
+// stores is needed.  Two buffers ping-pong: step s writes X[s&1] and reads X[(s-1)&1]; overwriting
+// X[s&1] at step s is safe because its previous content (step s-2) was read at the start of step
+// s-1, and a CTA can only be in step s once every CTA has published its step s-1 output, i.e. has
+// finished that read.  The buffers are zeroed before the launch (step numbers start at 1).
+__device__ __forceinline__ void ld_volatile_2x64(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
 {
-    named_bar_sync(1, NCONS);
-    if (ctid == 0) {
-        red_release_gpu(bar, 1u);
-        const unsigned want = epoch * gridDim.x;
-        unsigned long long t0 = 0;
-        for (uint32_t spins = 0; ld_acquire_gpu(bar) < want; ++spins) watchdog(spins, t0);
+    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+
+__device__ __forceinline__ void publish_delta(unsigned long long *xch, int i, float v, int step)
+{
+    const unsigned long long w = ((unsigned long long)(unsigned)step << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.global.u64 [%0], %1;" ::"l"(xch + i), "l"(w) : "memory");
+}
+
+// Stage delta_{s-1} in shared memory: from the plain start vector for s == 1, else from the
+// exchange buffer, waiting for every entry to carry step s-1.
+__device__ __forceinline__ void delta_wait_load(const PersistArgs &a, int s, float *sdelta, int ctid)
+{
+    const int Kp2 = a.Kp >> 1;
+    float2 *sd2 = reinterpret_cast<float2 *>(sdelta);
+    if (s == 1) {
+        const float2 *in2 = reinterpret_cast<const float2 *>(a.d_init);
+        for (int t = ctid; t < Kp2; t += NCONS) {
+            float2 v = __ldcg(in2 + t);
+            if (2 * t >= a.K) v.x = 0.f;  // padding lanes stay finite (hiT pads with -inf)
+            if (2 * t + 1 >= a.K) v.y = 0.f;
+            sd2[t] = v;
+        }
+    } else {
+        const unsigned long long *x = a.xch + (size_t)((s - 1) & 1) * a.Kp;
+        const unsigned want = (unsigned)(s - 1);
+        for (int t = ctid; t < Kp2; t += NCONS) {
+            float2 v = make_float2(0.f, 0.f);
+            const int k = 2 * t;
+            if (k < a.K) {
+                unsigned long long w0, w1, t0 = 0;
+                for (uint32_t spins = 0;; ++spins) {
+                    ld_volatile_2x64(x + k, w0, w1);
+                    if ((unsigned)(w0 >> 32) == want && (k + 1 >= a.K || (unsigned)(w1 >> 32) == want)) break;
+                    watchdog(spins * 64u + 63u, t0);
+                }
+                v.x = __uint_as_float((unsigned)w0);
+                if (k + 1 < a.K) v.y = __uint_as_float((unsigned)w1);
+            }
+            sd2[t] = v;
+        }
     }
     named_bar_sync(1, NCONS);
 }
@@ -217,8 +248,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Kp4 = a.Kp >> 2;
-    const int chunk4 = a.chunk >> 2;
-    const int nchunks = a.Kp / a.chunk;
+    const int nchunks = (a.Kp + a.chunk - 1) / a.chunk;
     const uint32_t stage_bytes = (uint32_t)a.chunk * 4u;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *empty = full + MAX_STAGES;
@@ -254,9 +284,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                         for (int c = 0; c < gcols; ++c, ++item) {
                             const uint32_t st = item % (uint32_t)a.nstage, use = item / (uint32_t)a.nstage;
                             if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
-                            mbar_expect_tx(&full[st], stage_bytes);
+                            const uint32_t bytes = (uint32_t)min(a.chunk, a.Kp - ch * a.chunk) * 4u;
+                            mbar_expect_tx(&full[st], bytes);
                             bulk_g2s(ring + (size_t)st * stage_bytes,
-                                     slab + ((size_t)(g0 + c) * a.Kp + (size_t)ch * a.chunk) * sizeof(float), stage_bytes,
+                                     slab + ((size_t)(g0 + c) * a.Kp + (size_t)ch * a.chunk) * sizeof(float), bytes,
                                      &full[st], pol, a.l2_hint != 0);
                             *issued = item + 1;
                         }
@@ -268,16 +299,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
     // ---------------- consumers ---------------------------------------------------------------
     const float *sdelta = reinterpret_cast<const float *>(sdelta4);
     for (int s = 1; s <= a.nsteps; ++s) {
-        const float *din = (s & 1) ? a.d0 : a.d1;
-        float *dout = (s & 1) ? a.d1 : a.d0;
+        unsigned long long *xout = a.xch + (size_t)(s & 1) * a.Kp;
+        const bool last_step = s == a.nsteps;
         const int j = a.L + s;
-        {
-            const float4 *din4 = reinterpret_cast<const float4 *>(din);
-            for (int t = tid; t < Kp4; t += NCONS) sdelta4[t] = __ldcg(din4 + t);
-        }
         const float *tmp_row = a.LBf + (size_t)__ldg(a.ob + j) * a.Kp;  // F:167
         const bool keep = j >= a.mid + 1;                                // F:242
-        named_bar_sync(1, NCONS);
+        delta_wait_load(a, s, reinterpret_cast<float *>(sdelta4), tid);
 
         for (int n0 = warp * CPW; n0 < ncols; n0 += NCW * CPW) {
             const bool two = n0 + 1 < ncols;
@@ -299,7 +326,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                 // "item started" implies the barrier is in the right phase.
                 {
                     unsigned long long t0 = 0;
-                    for (uint32_t spins = 0; *issued <= item0 + (two ? 1u : 0u); ++spins) watchdog(spins, t0);
+                    for (uint32_t spins = 0; *issued <= item0 + (two ? 1u : 0u); ++spins) {
+                        __nanosleep(40);
+                        watchdog(spins, t0);
+                    }
                 }
                 mbar_wait(&full[st0], (item0 / (uint32_t)a.nstage) & 1);
                 const float4 *p0 = reinterpret_cast<const float4 *>(ring + (size_t)st0 * stage_bytes);
@@ -309,9 +339,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                     mbar_wait(&full[st1], (item1 / (uint32_t)a.nstage) & 1);
                     p1 = reinterpret_cast<const float4 *>(ring + (size_t)st1 * stage_bytes);
                 }
-                const float4 *d4 = sdelta4 + (size_t)ch * chunk4;
+                const float4 *d4 = sdelta4 + (size_t)ch * (a.chunk >> 2);
+                const int len4 = min(a.chunk, a.Kp - ch * a.chunk) >> 2;
 #pragma unroll 4
-                for (int t = lane; t < chunk4; t += 32) {
+                for (int t = lane; t < len4; t += 32) {
                     const float4 d = d4[t];
                     const float4 h0 = p0[t];
                     const float4 h1 = p1[t];
@@ -347,18 +378,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             }
             const Best r0 = pending_finish(q0);
             if (lane == 0) {
-                dout[i0] = r0.x;
+                publish_delta(xout, i0, r0.x, s);
+                if (last_step) a.d_final[i0] = r0.x;
                 if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i0, r0.k);
             }
             if (two) {
                 const Best r1 = pending_finish(q1);
                 if (lane == 0) {
-                    dout[i1] = r1.x;
+                    publish_delta(xout, i1, r1.x, s);
+                    if (last_step) a.d_final[i1] = r1.x;
                     if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i1, r1.k);
                 }
             }
         }
-        grid_barrier(a.bar, (unsigned)s, tid);
+        named_bar_sync(1, NCONS);  // sdelta is overwritten by the next step's load
     }
 }
 
@@ -377,17 +410,20 @@ static int env_int(const char *name, int dflt)
 static int launch_persist(flashv_ctx *ctx, PersistArgs &a)
 {
     const int Kp = a.Kp;
-    a.chunk = Kp <= 4096 ? Kp : 4096;
-    while (Kp % a.chunk) a.chunk -= 128;  // Kp is a multiple of 128, so this ends at >= 128
+    int chunk = env_int("FLASHV_CHUNK", 2048);
+    chunk = chunk / 128 * 128;
+    if (chunk < 128) chunk = 128;
+    if (chunk > Kp) chunk = Kp;
+    a.chunk = chunk;
     const size_t fixed = persist_smem(Kp, 0, 0);
-    if (fixed + 2 * (size_t)a.chunk * 4 > (size_t)ctx->smem_optin) {
+    if (fixed + (size_t)(CPW + 1) * a.chunk * 4 > (size_t)ctx->smem_optin) {
         set_error("persistent engine: K=%d does not fit shared memory (%d bytes)", a.K, ctx->smem_optin);
         return FLASHV_ERR_ARG;
     }
     int nstage = (int)(((size_t)ctx->smem_optin - fixed) / ((size_t)a.chunk * 4));
     if (nstage > MAX_STAGES) nstage = MAX_STAGES;
     const int cap = env_int("FLASHV_STAGES", 0);
-    if (cap >= 2 && cap < nstage) nstage = cap;
+    if (cap >= CPW + 1 && cap < nstage) nstage = cap;
     a.nstage = nstage;
     a.l2_hint = env_int("FLASHV_L2_HINT", 1);
     const size_t smem = persist_smem(Kp, a.chunk, nstage);
@@ -401,8 +437,9 @@ static int launch_persist(flashv_ctx *ctx, PersistArgs &a)
     }
     int grid = ctx->sm_count;
     if (grid > a.K) grid = a.K;
-    FV_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), ctx->stream));
+    FV_CUDA(cudaMemsetAsync(a.xch, 0, (size_t)2 * a.Kp * sizeof(unsigned long long), ctx->stream));
     void *params[] = {(void *)&a};
+    // cooperative launch: every CTA polls data the others produce, so all must be co-resident
     FV_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NTHREADS), params, smem, ctx->stream));
     return FLASHV_OK;
 }
@@ -415,8 +452,9 @@ int persistent_pass(flashv_plan *p, const Pass &pass)
     a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.ob = p->d_ob;
     a.L = vd.L, a.nsteps = vd.R - vd.L, a.mid = vd.mid, a.psi_row = vd.psi_row;
-    a.d0 = p->d_delta, a.d1 = p->d_delta + (size_t)p->max_vec * m->Kp;
-    a.psi = p->d_psi, a.psi16 = p->psi16, a.bar = p->d_sync;
+    a.d_init = p->d_delta, a.d_final = p->d_delta + (size_t)p->max_vec * m->Kp;
+    a.xch = reinterpret_cast<unsigned long long *>(p->d_delta + (size_t)2 * p->max_vec * m->Kp);
+    a.psi = p->d_psi, a.psi16 = p->psi16;
     int rc = launch_persist(m->ctx, a);
     if (rc == FLASHV_OK) p->launches += 1;
     return rc;
@@ -432,9 +470,9 @@ int persistent_single_step(flashv_model *m, const float *d_in_dev, int o, float 
     PersistArgs a;
     a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.ob = dob, a.L = 0, a.nsteps = 1, a.mid = 0, a.psi_row = 0;
-    a.d0 = const_cast<float *>(d_in_dev), a.d1 = d_out_dev;
+    a.d_init = d_in_dev, a.d_final = d_out_dev;
+    a.xch = reinterpret_cast<unsigned long long *>(m->scratch_x);
     a.psi = psi_dev, a.psi16 = 0;
-    a.bar = reinterpret_cast<unsigned *>(m->scratch_i + 32);
     return launch_persist(ctx, a);
 }
 

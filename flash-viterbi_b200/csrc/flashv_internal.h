@@ -91,7 +91,8 @@ struct flashv_model {
     double *LBd = nullptr;    // [M][K]   log B (double), symbol-major — start vectors (F:142, F:220)
     double *LPi = nullptr;    // [K]      log Pi
     float *scratch_f = nullptr;   // test hooks: 2*Kp floats
-    int32_t *scratch_i = nullptr; // test hooks: Kp ints
+    int32_t *scratch_i = nullptr; // test hooks: 2*Kp ints
+    void *scratch_x = nullptr;    // test hooks: exchange buffers [2][Kp] x 8 B
     size_t bytes = 0;
     double prep_ms = 0;
     std::vector<flashv_plan *> plan_cache;  // owned; used by the one-call decodes
@@ -108,7 +109,7 @@ struct flashv_plan {
     int32_t *d_ob = nullptr;      // [batch][T]
     int32_t *d_ans = nullptr;     // [batch][T]
     float *d_score = nullptr;     // [batch]
-    float *d_delta = nullptr;     // [2][max_vec][Kp]
+    float *d_delta = nullptr;     // [2][max_vec][Kp] + exchange buffers [2][Kp] x 8 B of the persistent engine
     void *d_psi = nullptr;        // [max psi_rows][K] u16 or i32
     flashv::VecDesc *d_vecs = nullptr;
     uint8_t *d_ismid = nullptr;   // [T] 1 where a first-pass segment boundary sits

@@ -111,6 +111,7 @@ int tables_build(flashv_model *m, const float *A, const float *B, const float *P
     TB_CUDA(cudaMalloc(&m->LPi, (size_t)K * sizeof(double)));
     TB_CUDA(cudaMalloc(&m->scratch_f, (size_t)4 * Kp * sizeof(float)));
     TB_CUDA(cudaMalloc(&m->scratch_i, (size_t)2 * Kp * sizeof(int32_t)));
+    TB_CUDA(cudaMalloc(&m->scratch_x, (size_t)2 * Kp * 8));
     m->bytes = nA * sizeof(double) + (size_t)K * Kp * 4 + (size_t)M * Kp * 4 + (size_t)M * K * 8 + (size_t)K * 8 +
                (size_t)6 * Kp * 4;
     TB_CUDA(cudaMemcpyAsync(m->LAd, hLA, nA * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
