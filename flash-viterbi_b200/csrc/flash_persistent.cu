@@ -2,36 +2,39 @@
 // of nvviterNdivide, F:126-202, or a full-length task of nvviter, F:204-262) in ONE cooperative
 // launch, one CTA per SM.
 //
-//   * Each CTA owns a contiguous range of destination columns of hiT (K/gridDim of them), i.e. one
-//     contiguous ~K*Kp*4/gridDim byte slab that it re-reads every step — from L2 when the table
-//     fits (62.9 MB at K=3965 against 126 MB of L2; ncu: 97.7 % L2 hit rate, 0.25 % DRAM).
+//   * Each CTA owns a contiguous range of destination columns (K/gridDim of them) and re-reads their
+//     log-A entries every step — from L2 when the table fits (62.9 MB at K=3965 against 126 MB of
+//     L2; ncu: 97 % L2 hit rate, 0.25 % DRAM).  The table is stored CTA-tiled (hiC, tile_geom.h):
+//     per CTA, per chunk of TILE_CH source states, the chunk of every owned column back to back,
+//     so one step of one CTA is one linear stream and every ring stage is one contiguous bulk copy.
 //   * Warp NCW is the producer: one lane streams the slab through an NSTAGE-deep shared-memory ring
 //     with bulk TMA copies (cp.async.bulk ... mbarrier::complete_tx), running ahead across step
-//     boundaries since the table does not change — the ring refills while the CTAs sit in the grid
-//     barrier and reload delta.
-//   * Warps 0..NCW-1 are consumers.  A warp takes CPW columns at a time so one delta load from
-//     shared memory feeds CPW columns; lane l owns k = 4*(l+32u)+c and keeps four running maxima
-//     per column of the float estimate (FADD, FADD, FMNMX per update).  The exact (value, first
-//     index) comes from the double table for the few candidates inside the window
-//     (trellis_common.cuh): the candidates are found by re-scanning the winning chain in the
-//     shared-memory stage, their double loads are issued for all CPW columns before any is
-//     consumed, so a warp pays one HBM round trip per step.
-//   * Steps hand over through the delta vector itself (NaN-armed buffers polled from L2, see
+//     boundaries since the table does not change — the ring refills while the CTAs hand over.
+//   * Warps 0..NCW-1 are consumers and ALL of them work on every stage: warp w owns CPW fixed
+//     columns of the round (rows 2w, 2w+1 of the stage), lane l owns k = 4*(l+32u)+c and keeps four
+//     running maxima per column of the float estimate (FADD, FADD, FMNMX per update); a stage is
+//     released after NCW arrivals, so the ring is a true FIFO and no warp ever holds a stage longer
+//     than one pass over its two rows.  The exact (value, first index) comes from the double table
+//     for the few candidates inside the window (trellis_common.cuh): the winning chain is re-read
+//     from the tiled table (L2), the double loads of both columns are issued before either is
+//     consumed.
+//   * Steps hand over through the delta vector itself ({value, step} words polled from L2, see
 //     delta_wait_load): no grid barrier, no atomics.
 //   F: = /root/reference/src/FLASH_Viterbi_multithread.c
 #include <stdlib.h>
 
 #include "flashv_internal.h"
+#include "tile_geom.h"
 #include "trellis_common.cuh"
 
 namespace flashv {
 
-constexpr int NCW = 14;               // consumer warps
-constexpr int CPW = 2;                // columns a consumer warp processes together
+constexpr int NCW = TILE_RW / 2;      // consumer warps (14)
+constexpr int CPW = 2;                // columns a consumer warp owns per round
 constexpr int NCONS = NCW * 32;       // consumer threads
 constexpr int NTHREADS = NCONS + 32;  // + producer warp
 constexpr int MAX_STAGES = 64;
-constexpr int CTRL_BYTES = 2 * MAX_STAGES * 8 + 128;  // full[], empty[], the producer's issue counter
+constexpr int CTRL_BYTES = 2 * MAX_STAGES * 8;  // full[], empty[]
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,7 +113,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 struct PersistArgs {
-    const float *hiT;
+    const float *hiC;  // CTA-tiled (float)log A, tile_geom.h
     const double *LAd;
     const float *LBf;
     int K, Kp;
@@ -121,7 +124,6 @@ struct PersistArgs {
     unsigned long long *xch;  // [2][Kp] exchange buffers of {value, step} words, zeroed before the launch
     void *psi;
     int psi16;
-    int chunk;      // floats per ring stage (multiple of 128; the last chunk of a column may be shorter)
     int nstage;
     int l2_hint;
 };
@@ -213,11 +215,11 @@ __device__ __forceinline__ Best pending_finish(Pending &p)
     return b;
 }
 
-// Find the window candidates of column i (estimates from `col`, which may point into the
-// shared-memory stage or into hiT) and start their exact loads.
-__device__ __forceinline__ void scan_column(Pending &p, const float (&cm)[4], float tmp, const float *col,
-                                            const float *sdelta, const double *__restrict__ LAd, int K, int Kp, int i,
-                                            int lane)
+// Find the window candidates of column i (row rr of a round whose tiled block starts at `round_base`
+// and holds ncr columns) and start their exact loads.
+__device__ __forceinline__ void scan_column(Pending &p, const float (&cm)[4], float tmp,
+                                            const float *__restrict__ round_base, int ncr, int rr, const float *sdelta,
+                                            const double *__restrict__ LAd, int K, int Kp, int i, int lane)
 {
     p.acc = Best{-FLT_MAX, 0x7fffffff};
     p.has = false;
@@ -236,7 +238,7 @@ __device__ __forceinline__ void scan_column(Pending &p, const float (&cm)[4], fl
                 const int k = 4 * (w + 32 * u) + c;
                 if (k < K) {
                     const float pre = __fadd_rn(tmp, sdelta[k]);
-                    const float est = __fadd_rn(pre, col[k]);
+                    const float est = __fadd_rn(pre, __ldg(round_base + tile_round_off(Kp, ncr, rr, k)));
                     if (ford(est) >= thr) pending_push(p, pre, k, LAd + (size_t)k * K + i);
                 }
             }
@@ -248,56 +250,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Kp4 = a.Kp >> 2;
-    const int nchunks = (a.Kp + a.chunk - 1) / a.chunk;
-    const uint32_t stage_bytes = (uint32_t)a.chunk * 4u;
+    const int nk = (a.Kp + TILE_CH - 1) / TILE_CH;  // chunks per column
+    constexpr uint32_t STAGE_BYTES = TILE_RW * TILE_CH * 4u;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *empty = full + MAX_STAGES;
-    volatile uint32_t *issued = reinterpret_cast<volatile uint32_t *>(empty + MAX_STAGES);  // items the producer has started
     float4 *sdelta4 = reinterpret_cast<float4 *>(smem_raw + CTRL_BYTES);
     unsigned char *ring = reinterpret_cast<unsigned char *>(sdelta4 + Kp4);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, b = blockIdx.x;
-    const int c0 = (int)((long long)b * a.K / G), c1 = (int)((long long)(b + 1) * a.K / G);
-    const int ncols = c1 - c0;
+    const int c0 = tile_c0(a.K, G, b), ncols = tile_c0(a.K, G, b + 1) - c0;
+    const int nrounds = (ncols + TILE_RW - 1) / TILE_RW;
+    const float *slab = a.hiC + (size_t)c0 * a.Kp;  // this CTA's columns: ncols*Kp floats, in stream order
 
     if (tid == 0) {
-        for (int s = 0; s < a.nstage; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
-        *issued = 0;
+        for (int s = 0; s < a.nstage; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], NCW);
         mbar_fence_init();
     }
     __syncthreads();
 
     if (warp == NCW) {
-        // ---------------- producer: the slab of this CTA, once per step, through the ring --------
+        // ---------------- producer: the slab, once per step, linearly through the ring -----------
         if (lane == 0) {
             const uint64_t pol = policy_evict_last();
-            const unsigned char *slab = reinterpret_cast<const unsigned char *>(a.hiT + (size_t)c0 * a.Kp);
-            // item order = the order consumers need them: step, column group (CPW columns that one
-            // warp processes together), chunk, column within the group — a warp only ever waits
-            // for CPW consecutive items, so any ring depth >= CPW is deadlock-free
             uint32_t item = 0;
-            for (int s = 1; s <= a.nsteps; ++s)
-                for (int g0 = 0; g0 < ncols; g0 += CPW) {
-                    const int gcols = min(CPW, ncols - g0);
-                    for (int ch = 0; ch < nchunks; ++ch)
-                        for (int c = 0; c < gcols; ++c, ++item) {
-                            const uint32_t st = item % (uint32_t)a.nstage, use = item / (uint32_t)a.nstage;
-                            if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
-                            const uint32_t bytes = (uint32_t)min(a.chunk, a.Kp - ch * a.chunk) * 4u;
-                            mbar_expect_tx(&full[st], bytes);
-                            bulk_g2s(ring + (size_t)st * stage_bytes,
-                                     slab + ((size_t)(g0 + c) * a.Kp + (size_t)ch * a.chunk) * sizeof(float), bytes,
-                                     &full[st], pol, a.l2_hint != 0);
-                            *issued = item + 1;
-                        }
+            for (int s = 1; s <= a.nsteps; ++s) {
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(slab);
+                for (int rho = 0; rho < nrounds; ++rho) {
+                    const int ncr = min(TILE_RW, ncols - rho * TILE_RW);
+                    for (int u = 0; u < nk; ++u, ++item) {
+                        const uint32_t st = item % (uint32_t)a.nstage, use = item / (uint32_t)a.nstage;
+                        if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
+                        const uint32_t bytes = (uint32_t)(ncr * min(TILE_CH, a.Kp - u * TILE_CH)) * 4u;
+                        mbar_expect_tx(&full[st], bytes);
+                        bulk_g2s(ring + (size_t)st * STAGE_BYTES, src, bytes, &full[st], pol, a.l2_hint != 0);
+                        src += bytes;
+                    }
                 }
+            }
         }
         return;
     }
 
     // ---------------- consumers ---------------------------------------------------------------
     const float *sdelta = reinterpret_cast<const float *>(sdelta4);
+    uint32_t item = 0;  // every consumer warp visits every ring item, in the producer's order
     for (int s = 1; s <= a.nsteps; ++s) {
         unsigned long long *xout = a.xch + (size_t)(s & 1) * a.Kp;
         const bool last_step = s == a.nsteps;
@@ -306,83 +303,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
         const bool keep = j >= a.mid + 1;                                // F:242
         delta_wait_load(a, s, reinterpret_cast<float *>(sdelta4), tid);
 
-        for (int n0 = warp * CPW; n0 < ncols; n0 += NCW * CPW) {
-            const bool two = n0 + 1 < ncols;
-            const int i0 = c0 + n0, i1 = two ? i0 + 1 : i0;
+        for (int rho = 0; rho < nrounds; ++rho) {
+            const int ncr = min(TILE_RW, ncols - rho * TILE_RW);
+            const int rr0 = warp * CPW, rr1 = rr0 + 1;
+            const bool have0 = rr0 < ncr, have1 = rr1 < ncr;
+            const int i0 = c0 + rho * TILE_RW + (have0 ? rr0 : 0), i1 = c0 + rho * TILE_RW + (have1 ? rr1 : 0);
             const float tmp0 = __ldg(tmp_row + i0), tmp1 = __ldg(tmp_row + i1);
             float cm0[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             float cm1[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            const float *last0 = nullptr, *last1 = nullptr;
-            uint32_t st0 = 0, st1 = 0;
-            for (int ch = 0; ch < nchunks; ++ch) {
-                // ring items are numbered in the producer's order: step, group, chunk, column in group
-                const uint32_t item0 = (uint32_t)((s - 1) * ncols + n0) * (uint32_t)nchunks + (uint32_t)ch * (two ? 2u : 1u);
-                const uint32_t item1 = item0 + 1u;
-                st0 = item0 % (uint32_t)a.nstage;
-                // A parity wait is only meaningful once the stage is in the phase of THIS use: with more
-                // columns demanded at once than ring stages, a warp can get here before the stage's
-                // previous use has even landed, and try_wait would then report the older phase as done.
-                // The producer starts item i only after use i-nstage of the stage was released, so
-                // "item started" implies the barrier is in the right phase.
-                {
-                    unsigned long long t0 = 0;
-                    for (uint32_t spins = 0; *issued <= item0 + (two ? 1u : 0u); ++spins) {
-                        __nanosleep(40);
-                        watchdog(spins, t0);
+            for (int u = 0; u < nk; ++u, ++item) {
+                const uint32_t st = item % (uint32_t)a.nstage;
+                mbar_wait(&full[st], (item / (uint32_t)a.nstage) & 1);
+                if (have0) {
+                    const int len4 = min(TILE_CH, a.Kp - u * TILE_CH) >> 2;
+                    const float4 *stage4 = reinterpret_cast<const float4 *>(ring + (size_t)st * STAGE_BYTES);
+                    const float4 *p0 = stage4 + (size_t)rr0 * len4;
+                    const float4 *p1 = have1 ? stage4 + (size_t)rr1 * len4 : p0;
+                    const float4 *d4 = sdelta4 + (size_t)u * (TILE_CH >> 2);
+#pragma unroll 2
+                    for (int t = lane; t < len4; t += 32) {
+                        const float4 d = d4[t];
+                        const float4 h0 = p0[t];
+                        const float4 h1 = p1[t];
+                        cm0[0] = fmaxf(cm0[0], __fadd_rn(__fadd_rn(tmp0, d.x), h0.x));
+                        cm0[1] = fmaxf(cm0[1], __fadd_rn(__fadd_rn(tmp0, d.y), h0.y));
+                        cm0[2] = fmaxf(cm0[2], __fadd_rn(__fadd_rn(tmp0, d.z), h0.z));
+                        cm0[3] = fmaxf(cm0[3], __fadd_rn(__fadd_rn(tmp0, d.w), h0.w));
+                        cm1[0] = fmaxf(cm1[0], __fadd_rn(__fadd_rn(tmp1, d.x), h1.x));
+                        cm1[1] = fmaxf(cm1[1], __fadd_rn(__fadd_rn(tmp1, d.y), h1.y));
+                        cm1[2] = fmaxf(cm1[2], __fadd_rn(__fadd_rn(tmp1, d.z), h1.z));
+                        cm1[3] = fmaxf(cm1[3], __fadd_rn(__fadd_rn(tmp1, d.w), h1.w));
                     }
                 }
-                mbar_wait(&full[st0], (item0 / (uint32_t)a.nstage) & 1);
-                const float4 *p0 = reinterpret_cast<const float4 *>(ring + (size_t)st0 * stage_bytes);
-                const float4 *p1 = p0;
-                if (two) {
-                    st1 = item1 % (uint32_t)a.nstage;
-                    mbar_wait(&full[st1], (item1 / (uint32_t)a.nstage) & 1);
-                    p1 = reinterpret_cast<const float4 *>(ring + (size_t)st1 * stage_bytes);
-                }
-                const float4 *d4 = sdelta4 + (size_t)ch * (a.chunk >> 2);
-                const int len4 = min(a.chunk, a.Kp - ch * a.chunk) >> 2;
-#pragma unroll 4
-                for (int t = lane; t < len4; t += 32) {
-                    const float4 d = d4[t];
-                    const float4 h0 = p0[t];
-                    const float4 h1 = p1[t];
-                    cm0[0] = fmaxf(cm0[0], __fadd_rn(__fadd_rn(tmp0, d.x), h0.x));
-                    cm0[1] = fmaxf(cm0[1], __fadd_rn(__fadd_rn(tmp0, d.y), h0.y));
-                    cm0[2] = fmaxf(cm0[2], __fadd_rn(__fadd_rn(tmp0, d.z), h0.z));
-                    cm0[3] = fmaxf(cm0[3], __fadd_rn(__fadd_rn(tmp0, d.w), h0.w));
-                    cm1[0] = fmaxf(cm1[0], __fadd_rn(__fadd_rn(tmp1, d.x), h1.x));
-                    cm1[1] = fmaxf(cm1[1], __fadd_rn(__fadd_rn(tmp1, d.y), h1.y));
-                    cm1[2] = fmaxf(cm1[2], __fadd_rn(__fadd_rn(tmp1, d.z), h1.z));
-                    cm1[3] = fmaxf(cm1[3], __fadd_rn(__fadd_rn(tmp1, d.w), h1.w));
-                }
-                last0 = reinterpret_cast<const float *>(p0);
-                last1 = reinterpret_cast<const float *>(p1);
-                if (ch + 1 < nchunks) {  // multi-chunk columns re-scan from hiT, so stages can go now
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(&empty[st0]);
-                        if (two) mbar_arrive(&empty[st1]);
-                    }
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st]);
             }
-            // candidates: from the stage when it still holds the whole column, else from hiT (L2)
-            const float *col0 = nchunks == 1 ? last0 : a.hiT + (size_t)i0 * a.Kp;
-            const float *col1 = nchunks == 1 ? last1 : a.hiT + (size_t)i1 * a.Kp;
+            if (!have0) continue;  // warp-uniform
+            const float *round_base = slab + (size_t)rho * TILE_RW * a.Kp;
             Pending q0, q1;
-            scan_column(q0, cm0, tmp0, col0, sdelta, a.LAd, a.K, a.Kp, i0, lane);
-            if (two) scan_column(q1, cm1, tmp1, col1, sdelta, a.LAd, a.K, a.Kp, i1, lane);
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&empty[st0]);
-                if (two) mbar_arrive(&empty[st1]);
-            }
+            scan_column(q0, cm0, tmp0, round_base, ncr, rr0, sdelta, a.LAd, a.K, a.Kp, i0, lane);
+            if (have1) scan_column(q1, cm1, tmp1, round_base, ncr, rr1, sdelta, a.LAd, a.K, a.Kp, i1, lane);
             const Best r0 = pending_finish(q0);
             if (lane == 0) {
                 publish_delta(xout, i0, r0.x, s);
                 if (last_step) a.d_final[i0] = r0.x;
                 if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i0, r0.k);
             }
-            if (two) {
+            if (have1) {
                 const Best r1 = pending_finish(q1);
                 if (lane == 0) {
                     publish_delta(xout, i1, r1.x, s);
@@ -396,9 +363,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-static size_t persist_smem(int Kp, int chunk, int nstage)
+static size_t persist_smem(int Kp, int nstage)
 {
-    return CTRL_BYTES + (size_t)Kp * 4 + (size_t)nstage * chunk * 4;
+    return CTRL_BYTES + (size_t)Kp * 4 + (size_t)nstage * TILE_RW * TILE_CH * 4;
 }
 
 static int env_int(const char *name, int dflt)
@@ -407,26 +374,22 @@ static int env_int(const char *name, int dflt)
     return e ? atoi(e) : dflt;
 }
 
-static int launch_persist(flashv_ctx *ctx, PersistArgs &a)
+static int launch_persist(flashv_model *m, PersistArgs &a)
 {
+    flashv_ctx *ctx = m->ctx;
     const int Kp = a.Kp;
-    int chunk = env_int("FLASHV_CHUNK", 2048);
-    chunk = chunk / 128 * 128;
-    if (chunk < 128) chunk = 128;
-    if (chunk > Kp) chunk = Kp;
-    a.chunk = chunk;
-    const size_t fixed = persist_smem(Kp, 0, 0);
-    if (fixed + (size_t)(CPW + 1) * a.chunk * 4 > (size_t)ctx->smem_optin) {
+    const size_t fixed = persist_smem(Kp, 0);
+    if (fixed + 2 * (size_t)TILE_RW * TILE_CH * 4 > (size_t)ctx->smem_optin) {
         set_error("persistent engine: K=%d does not fit shared memory (%d bytes)", a.K, ctx->smem_optin);
         return FLASHV_ERR_ARG;
     }
-    int nstage = (int)(((size_t)ctx->smem_optin - fixed) / ((size_t)a.chunk * 4));
+    int nstage = (int)(((size_t)ctx->smem_optin - fixed) / ((size_t)TILE_RW * TILE_CH * 4));
     if (nstage > MAX_STAGES) nstage = MAX_STAGES;
     const int cap = env_int("FLASHV_STAGES", 0);
-    if (cap >= CPW + 1 && cap < nstage) nstage = cap;
+    if (cap >= 2 && cap < nstage) nstage = cap;
     a.nstage = nstage;
     a.l2_hint = env_int("FLASHV_L2_HINT", 1);
-    const size_t smem = persist_smem(Kp, a.chunk, nstage);
+    const size_t smem = persist_smem(Kp, nstage);
     const void *fn = (const void *)k_flash_persist;
     FV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -435,12 +398,11 @@ static int launch_persist(flashv_ctx *ctx, PersistArgs &a)
         set_error("persistent engine: kernel does not fit one CTA per SM");
         return FLASHV_ERR_CUDA;
     }
-    int grid = ctx->sm_count;
-    if (grid > a.K) grid = a.K;
     FV_CUDA(cudaMemsetAsync(a.xch, 0, (size_t)2 * a.Kp * sizeof(unsigned long long), ctx->stream));
     void *params[] = {(void *)&a};
-    // cooperative launch: every CTA polls data the others produce, so all must be co-resident
-    FV_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NTHREADS), params, smem, ctx->stream));
+    // cooperative launch: every CTA polls data the others produce, so all must be co-resident;
+    // the grid is the one the tiled table was laid out for
+    FV_CUDA(cudaLaunchCooperativeKernel(fn, dim3(m->tile_G), dim3(NTHREADS), params, smem, ctx->stream));
     return FLASHV_OK;
 }
 
@@ -449,13 +411,13 @@ int persistent_pass(flashv_plan *p, const Pass &pass)
     flashv_model *m = p->model;
     const VecDesc &vd = pass.first_vec;  // the pass has exactly one vector (batch == 1)
     PersistArgs a;
-    a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+    a.hiC = m->hiC, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.ob = p->d_ob;
     a.L = vd.L, a.nsteps = vd.R - vd.L, a.mid = vd.mid, a.psi_row = vd.psi_row;
     a.d_init = p->d_delta, a.d_final = p->d_delta + (size_t)p->max_vec * m->Kp;
     a.xch = reinterpret_cast<unsigned long long *>(p->d_delta + (size_t)2 * p->max_vec * m->Kp);
     a.psi = p->d_psi, a.psi16 = p->psi16;
-    int rc = launch_persist(m->ctx, a);
+    int rc = launch_persist(m, a);
     if (rc == FLASHV_OK) p->launches += 1;
     return rc;
 }
@@ -468,12 +430,12 @@ int persistent_single_step(flashv_model *m, const float *d_in_dev, int o, float 
     FV_CUDA(cudaMemcpyAsync(dob, hob, sizeof(hob), cudaMemcpyHostToDevice, ctx->stream));
     FV_CUDA(cudaStreamSynchronize(ctx->stream));
     PersistArgs a;
-    a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+    a.hiC = m->hiC, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.ob = dob, a.L = 0, a.nsteps = 1, a.mid = 0, a.psi_row = 0;
     a.d_init = d_in_dev, a.d_final = d_out_dev;
     a.xch = reinterpret_cast<unsigned long long *>(m->scratch_x);
     a.psi = psi_dev, a.psi16 = 0;
-    return launch_persist(ctx, a);
+    return launch_persist(m, a);
 }
 
 }  // namespace flashv

@@ -86,6 +86,8 @@ struct flashv_model {
     int K = 0, M = 0;
     int Kp = 0;               // K rounded up to a multiple of 128 (one warp x float4)
     float *hiT = nullptr;     // [K][Kp]  (float)log A, destination-major: hiT[i][k] = log A[k][i]; pad = -inf
+    float *hiC = nullptr;     // K*Kp     the same, CTA-tiled for the persistent engine (tile_geom.h)
+    int tile_G = 0;           // grid the tiling was built for (min(#SM, K))
     double *LAd = nullptr;    // [K][K]   log A, source-major as the reference stores A (F:27)
     float *LBf = nullptr;     // [M][Kp]  (float)log B, symbol-major: LBf[o][i] — the per-step "tmp" (F:167)
     double *LBd = nullptr;    // [M][K]   log B (double), symbol-major — start vectors (F:142, F:220)

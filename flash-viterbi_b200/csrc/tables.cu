@@ -9,6 +9,7 @@
 //                      start vectors (F:220 reads row Ans[L-1])
 //   hiT [i][k] float   destination-major, padded to Kp: the stream the trellis kernels read —
 //                      the max over k for one destination i is one contiguous run
+//   hiC        float   the same numbers CTA-tiled for the persistent engine (tile_geom.h)
 //   LBf [o][i] float   the per-step "tmp" (F:167), symbol-major so one step reads one row
 //   LBd [o][i] double  start vectors (F:142, F:220)
 //   LPi [i]    double
@@ -22,6 +23,7 @@
 #include <vector>
 
 #include "flashv_internal.h"
+#include "tile_geom.h"
 
 namespace flashv {
 
@@ -42,6 +44,17 @@ __global__ void k_transpose_to_f32(const double *__restrict__ LAd, float *__rest
         int i = i0 + r, k = k0 + threadIdx.x;
         if (i < K && k < Kp) hiT[(size_t)i * Kp + k] = tile[threadIdx.x][r];
     }
+}
+
+// hiC: the same numbers CTA-tiled for the persistent engine (tile_geom.h).  One thread per (k, i),
+// reads coalesced along i from the hiT-independent double table, scattered 4-byte writes.
+__global__ void k_build_tiled(const double *__restrict__ LAd, float *__restrict__ hiC, int K, int Kp, int G)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i >= K) return;
+    const float v = k < K ? __double2float_rn(LAd[(size_t)k * K + i]) : -INFINITY;
+    hiC[tile_off(K, Kp, G, i, k)] = v;
 }
 
 static bool in_unit(const float *p, size_t n)
@@ -106,13 +119,14 @@ int tables_build(flashv_model *m, const float *A, const float *B, const float *P
     }
     TB_CUDA(cudaMalloc(&m->LAd, nA * sizeof(double)));
     TB_CUDA(cudaMalloc(&m->hiT, (size_t)K * Kp * sizeof(float)));
+    TB_CUDA(cudaMalloc(&m->hiC, (size_t)K * Kp * sizeof(float)));
     TB_CUDA(cudaMalloc(&m->LBf, (size_t)M * Kp * sizeof(float)));
     TB_CUDA(cudaMalloc(&m->LBd, (size_t)M * K * sizeof(double)));
     TB_CUDA(cudaMalloc(&m->LPi, (size_t)K * sizeof(double)));
     TB_CUDA(cudaMalloc(&m->scratch_f, (size_t)4 * Kp * sizeof(float)));
     TB_CUDA(cudaMalloc(&m->scratch_i, (size_t)2 * Kp * sizeof(int32_t)));
     TB_CUDA(cudaMalloc(&m->scratch_x, (size_t)2 * Kp * 8));
-    m->bytes = nA * sizeof(double) + (size_t)K * Kp * 4 + (size_t)M * Kp * 4 + (size_t)M * K * 8 + (size_t)K * 8 +
+    m->bytes = nA * sizeof(double) + (size_t)2 * K * Kp * 4 + (size_t)M * Kp * 4 + (size_t)M * K * 8 + (size_t)K * 8 +
                (size_t)6 * Kp * 4;
     TB_CUDA(cudaMemcpyAsync(m->LAd, hLA, nA * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     TB_CUDA(cudaMemcpyAsync(m->LBf, hLBf.data(), hLBf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -121,6 +135,9 @@ int tables_build(flashv_model *m, const float *A, const float *B, const float *P
     TB_CUDA(cudaMemsetAsync(m->scratch_f, 0, (size_t)4 * Kp * sizeof(float), ctx->stream));
     dim3 grid((K + 31) / 32, (Kp + 31) / 32), block(32, 8);
     k_transpose_to_f32<<<grid, block, 0, ctx->stream>>>(m->LAd, m->hiT, K, Kp);
+    TB_CUDA(cudaGetLastError());
+    m->tile_G = ctx->sm_count < K ? ctx->sm_count : K;
+    k_build_tiled<<<dim3((K + 255) / 256, Kp), 256, 0, ctx->stream>>>(m->LAd, m->hiC, K, Kp, m->tile_G);
     TB_CUDA(cudaGetLastError());
     TB_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef TB_CUDA

@@ -15,7 +15,7 @@ timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_persistent_n
 timeout 120 python bench.py --steps 5 --warmup 3 --segments 8 --no-cpu > gpurun_out/bench_persistent_n8.log 2>&1
 timeout 120 python bench.py --steps 5 --warmup 3 --segments 127 --no-cpu > gpurun_out/bench_persistent_n127.log 2>&1
 timeout 120 python bench.py --steps 5 --warmup 3 --engine step --no-cpu > gpurun_out/bench_step_n64.log 2>&1
-for c in 1024 3968; do
+for c in; do
 FLASHV_CHUNK=$c timeout 120 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_persistent_chunk$c.log 2>&1
 done
 tail -2 gpurun_out/smoke.log; tail -1 gpurun_out/bench_persistent_n64.log
