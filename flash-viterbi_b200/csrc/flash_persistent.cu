@@ -215,22 +215,76 @@ __device__ __forceinline__ Best pending_finish(Pending &p)
     return b;
 }
 
-// Find the window candidates of column i (row rr of a round whose tiled block starts at `round_base`
-// and holds ncr columns) and start their exact loads.
-__device__ __forceinline__ void scan_column(Pending &p, const float (&cm)[4], float tmp,
+// Window scan of one column, split in two so that the L2 reads of several columns overlap:
+// scan_fetch() finds the chains whose maximum lies inside the window and loads, per lane, the
+// estimate inputs of (up to) SCAN_SLOTS chain elements from the tiled table; scan_commit() compares
+// them against the window and starts the exact double loads.  Anything that does not fit the slots
+// (several chains inside the window, or chains longer than 32 elements) takes the slow path
+// inside scan_commit(), which re-reads synchronously.
+constexpr int SCAN_SLOTS = 2;
+struct Scan {
+    float hi0, hi1;  // slot s holds element `lane` of the s-th chain inside the window
+    int k0, k1;      // its source state, or -1 if this lane has no element in that slot
+    int thr;         // window threshold (ordinal), warp-uniform
+    unsigned overflow;  // warp-uniform: some chain did not fit the slots
+    bool dead;       // warp-uniform: no finite estimate in the column
+};
+
+__device__ __forceinline__ void scan_fetch(Scan &sc, const float (&cm)[4], const float *__restrict__ round_base,
+                                           int ncr, int rr, int K, int Kp, int lane)
+{
+    sc.k0 = sc.k1 = -1, sc.hi0 = sc.hi1 = 0.f, sc.overflow = 0;
+    const float top = warp_max(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
+    sc.dead = !(top > -FLT_MAX);
+    sc.thr = ford(top) - WINDOW_STEPS;
+    if (sc.dead) return;
+    const int chain_len = Kp >> 7;
+    int used = 0;  // warp-uniform count of chains taken
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned hit = __ballot_sync(FULL_MASK, ford(cm[c]) >= sc.thr);
+        while (hit) {
+            const int w = __ffs(hit) - 1;
+            hit &= hit - 1;
+            if (used >= SCAN_SLOTS || chain_len > 32) {
+                sc.overflow = 1;
+                continue;
+            }
+            const int k = 4 * (w + 32 * lane) + c;  // element `lane` of chain (w, c)
+            if (lane < chain_len && k < K) {
+                const float h = __ldg(round_base + tile_round_off(Kp, ncr, rr, k));
+                if (used == 0) sc.hi0 = h, sc.k0 = k;
+                else sc.hi1 = h, sc.k1 = k;
+            }
+            ++used;
+        }
+    }
+}
+
+__device__ __forceinline__ void scan_commit(Pending &p, const Scan &sc, const float (&cm)[4], float tmp,
                                             const float *__restrict__ round_base, int ncr, int rr, const float *sdelta,
                                             const double *__restrict__ LAd, int K, int Kp, int i, int lane)
 {
     p.acc = Best{-FLT_MAX, 0x7fffffff};
     p.has = false;
     p.la = 0.0, p.pre = 0.f, p.k = 0;
-    const float top = warp_max(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
-    if (!(top > -FLT_MAX)) return;  // dead column (warp-uniform)
-    const int thr = ford(top) - WINDOW_STEPS;
+    if (sc.dead) return;
+    if (!sc.overflow) {
+        if (sc.k0 >= 0) {
+            const float pre = __fadd_rn(tmp, sdelta[sc.k0]);
+            if (ford(__fadd_rn(pre, sc.hi0)) >= sc.thr) pending_push(p, pre, sc.k0, LAd + (size_t)sc.k0 * K + i);
+        }
+        if (sc.k1 >= 0) {
+            const float pre = __fadd_rn(tmp, sdelta[sc.k1]);
+            if (ford(__fadd_rn(pre, sc.hi1)) >= sc.thr) pending_push(p, pre, sc.k1, LAd + (size_t)sc.k1 * K + i);
+        }
+        return;
+    }
+    // slow path: every chain inside the window, element by element
     const int chain_len = Kp >> 7;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        unsigned hit = __ballot_sync(FULL_MASK, ford(cm[c]) >= thr);
+        unsigned hit = __ballot_sync(FULL_MASK, ford(cm[c]) >= sc.thr);
         while (hit) {
             const int w = __ffs(hit) - 1;
             hit &= hit - 1;
@@ -239,7 +293,7 @@ __device__ __forceinline__ void scan_column(Pending &p, const float (&cm)[4], fl
                 if (k < K) {
                     const float pre = __fadd_rn(tmp, sdelta[k]);
                     const float est = __fadd_rn(pre, __ldg(round_base + tile_round_off(Kp, ncr, rr, k)));
-                    if (ford(est) >= thr) pending_push(p, pre, k, LAd + (size_t)k * K + i);
+                    if (ford(est) >= sc.thr) pending_push(p, pre, k, LAd + (size_t)k * K + i);
                 }
             }
         }
@@ -273,18 +327,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
         // ---------------- producer: the slab, once per step, linearly through the ring -----------
         if (lane == 0) {
             const uint64_t pol = policy_evict_last();
-            uint32_t item = 0;
+            int st = 0;
+            uint32_t use = 0;  // how often the ring has wrapped: stage st is being filled for the use-th time
             for (int s = 1; s <= a.nsteps; ++s) {
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(slab);
                 for (int rho = 0; rho < nrounds; ++rho) {
                     const int ncr = min(TILE_RW, ncols - rho * TILE_RW);
-                    for (int u = 0; u < nk; ++u, ++item) {
-                        const uint32_t st = item % (uint32_t)a.nstage, use = item / (uint32_t)a.nstage;
+                    for (int u = 0; u < nk; ++u) {
                         if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
                         const uint32_t bytes = (uint32_t)(ncr * min(TILE_CH, a.Kp - u * TILE_CH)) * 4u;
                         mbar_expect_tx(&full[st], bytes);
                         bulk_g2s(ring + (size_t)st * STAGE_BYTES, src, bytes, &full[st], pol, a.l2_hint != 0);
                         src += bytes;
+                        if (++st == a.nstage) st = 0, ++use;
                     }
                 }
             }
@@ -294,7 +349,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
 
     // ---------------- consumers ---------------------------------------------------------------
     const float *sdelta = reinterpret_cast<const float *>(sdelta4);
-    uint32_t item = 0;  // every consumer warp visits every ring item, in the producer's order
+    int st = 0;           // every consumer warp visits every ring item, in the producer's order
+    uint32_t parity = 0;  // parity of the ring wrap count = phase parity to wait for
+    const int nk_full = a.Kp / TILE_CH;  // chunks of exactly TILE_CH states; at most one shorter chunk follows
     for (int s = 1; s <= a.nsteps; ++s) {
         unsigned long long *xout = a.xch + (size_t)(s & 1) * a.Kp;
         const bool last_step = s == a.nsteps;
@@ -311,38 +368,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             const float tmp0 = __ldg(tmp_row + i0), tmp1 = __ldg(tmp_row + i1);
             float cm0[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             float cm1[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            for (int u = 0; u < nk; ++u, ++item) {
-                const uint32_t st = item % (uint32_t)a.nstage;
-                mbar_wait(&full[st], (item / (uint32_t)a.nstage) & 1);
+            // row offsets inside a full stage, in float4 units; a duplicate row stands in for a missing one
+            const int row0 = (have0 ? rr0 : 0) * (TILE_CH >> 2) + lane;
+            const int row1 = (have1 ? rr1 : (have0 ? rr0 : 0)) * (TILE_CH >> 2) + lane;
+            const float4 *d4 = sdelta4 + lane;
+            for (int u = 0; u < nk; ++u) {
+                const float4 *stage4 = reinterpret_cast<const float4 *>(ring + (size_t)st * STAGE_BYTES);
+                mbar_wait(&full[st], parity);
                 if (have0) {
-                    const int len4 = min(TILE_CH, a.Kp - u * TILE_CH) >> 2;
-                    const float4 *stage4 = reinterpret_cast<const float4 *>(ring + (size_t)st * STAGE_BYTES);
-                    const float4 *p0 = stage4 + (size_t)rr0 * len4;
-                    const float4 *p1 = have1 ? stage4 + (size_t)rr1 * len4 : p0;
-                    const float4 *d4 = sdelta4 + (size_t)u * (TILE_CH >> 2);
-#pragma unroll 2
-                    for (int t = lane; t < len4; t += 32) {
-                        const float4 d = d4[t];
-                        const float4 h0 = p0[t];
-                        const float4 h1 = p1[t];
-                        cm0[0] = fmaxf(cm0[0], __fadd_rn(__fadd_rn(tmp0, d.x), h0.x));
-                        cm0[1] = fmaxf(cm0[1], __fadd_rn(__fadd_rn(tmp0, d.y), h0.y));
-                        cm0[2] = fmaxf(cm0[2], __fadd_rn(__fadd_rn(tmp0, d.z), h0.z));
-                        cm0[3] = fmaxf(cm0[3], __fadd_rn(__fadd_rn(tmp0, d.w), h0.w));
-                        cm1[0] = fmaxf(cm1[0], __fadd_rn(__fadd_rn(tmp1, d.x), h1.x));
-                        cm1[1] = fmaxf(cm1[1], __fadd_rn(__fadd_rn(tmp1, d.y), h1.y));
-                        cm1[2] = fmaxf(cm1[2], __fadd_rn(__fadd_rn(tmp1, d.z), h1.z));
-                        cm1[3] = fmaxf(cm1[3], __fadd_rn(__fadd_rn(tmp1, d.w), h1.w));
+                    if (u < nk_full) {
+#pragma unroll
+                        for (int it = 0; it < TILE_CH / 128; ++it) {
+                            const float4 d = d4[it * 32];
+                            const float4 h0 = stage4[row0 + it * 32];
+                            const float4 h1 = stage4[row1 + it * 32];
+                            cm0[0] = fmaxf(cm0[0], __fadd_rn(__fadd_rn(tmp0, d.x), h0.x));
+                            cm0[1] = fmaxf(cm0[1], __fadd_rn(__fadd_rn(tmp0, d.y), h0.y));
+                            cm0[2] = fmaxf(cm0[2], __fadd_rn(__fadd_rn(tmp0, d.z), h0.z));
+                            cm0[3] = fmaxf(cm0[3], __fadd_rn(__fadd_rn(tmp0, d.w), h0.w));
+                            cm1[0] = fmaxf(cm1[0], __fadd_rn(__fadd_rn(tmp1, d.x), h1.x));
+                            cm1[1] = fmaxf(cm1[1], __fadd_rn(__fadd_rn(tmp1, d.y), h1.y));
+                            cm1[2] = fmaxf(cm1[2], __fadd_rn(__fadd_rn(tmp1, d.z), h1.z));
+                            cm1[3] = fmaxf(cm1[3], __fadd_rn(__fadd_rn(tmp1, d.w), h1.w));
+                        }
+                    } else {  // the short last chunk: rows are len4 float4 apart
+                        const int len4 = (a.Kp - u * TILE_CH) >> 2;
+                        const float4 *p0 = stage4 + (size_t)rr0 * len4;
+                        const float4 *p1 = have1 ? stage4 + (size_t)rr1 * len4 : p0;
+                        for (int t = lane; t < len4; t += 32) {
+                            const float4 d = d4[t - lane];
+                            const float4 h0 = p0[t];
+                            const float4 h1 = p1[t];
+                            cm0[0] = fmaxf(cm0[0], __fadd_rn(__fadd_rn(tmp0, d.x), h0.x));
+                            cm0[1] = fmaxf(cm0[1], __fadd_rn(__fadd_rn(tmp0, d.y), h0.y));
+                            cm0[2] = fmaxf(cm0[2], __fadd_rn(__fadd_rn(tmp0, d.z), h0.z));
+                            cm0[3] = fmaxf(cm0[3], __fadd_rn(__fadd_rn(tmp0, d.w), h0.w));
+                            cm1[0] = fmaxf(cm1[0], __fadd_rn(__fadd_rn(tmp1, d.x), h1.x));
+                            cm1[1] = fmaxf(cm1[1], __fadd_rn(__fadd_rn(tmp1, d.y), h1.y));
+                            cm1[2] = fmaxf(cm1[2], __fadd_rn(__fadd_rn(tmp1, d.z), h1.z));
+                            cm1[3] = fmaxf(cm1[3], __fadd_rn(__fadd_rn(tmp1, d.w), h1.w));
+                        }
                     }
                 }
+                d4 += TILE_CH >> 2;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[st]);
+                if (++st == a.nstage) st = 0, parity ^= 1;
             }
             if (!have0) continue;  // warp-uniform
             const float *round_base = slab + (size_t)rho * TILE_RW * a.Kp;
             Pending q0, q1;
-            scan_column(q0, cm0, tmp0, round_base, ncr, rr0, sdelta, a.LAd, a.K, a.Kp, i0, lane);
-            if (have1) scan_column(q1, cm1, tmp1, round_base, ncr, rr1, sdelta, a.LAd, a.K, a.Kp, i1, lane);
+            Scan s0, s1;
+            scan_fetch(s0, cm0, round_base, ncr, rr0, a.K, a.Kp, lane);
+            if (have1) scan_fetch(s1, cm1, round_base, ncr, rr1, a.K, a.Kp, lane);
+            scan_commit(q0, s0, cm0, tmp0, round_base, ncr, rr0, sdelta, a.LAd, a.K, a.Kp, i0, lane);
+            if (have1) scan_commit(q1, s1, cm1, tmp1, round_base, ncr, rr1, sdelta, a.LAd, a.K, a.Kp, i1, lane);
             const Best r0 = pending_finish(q0);
             if (lane == 0) {
                 publish_delta(xout, i0, r0.x, s);
