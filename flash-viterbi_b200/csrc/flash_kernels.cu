@@ -119,20 +119,41 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
                 }
             }
         }
+        // exact (value, first index) of the RI x QB pairs, their memory round trips overlapped
+        {
+            constexpr int P = RI * QB;
+            float ptmp[P];
+            const float *pcol[P];
+            const float *pdelta[P];
+            int picol[P];
+            float pcm[P][4];
+            Best res[P];
 #pragma unroll
-        for (int r = 0; r < RI; ++r) {
-            if (ibase + r >= a.K) continue;  // warp-uniform
-            const int i = ibase + r;
-            const float *col = a.hiT + (size_t)i * a.Kp;
+            for (int r = 0; r < RI; ++r)
 #pragma unroll
-            for (int q = 0; q < QB; ++q) {
-                if (v0 + q >= a.nact) continue;  // warp-uniform
-                const Best b = resolve_column(cm[r][q], tmp[r][q], col, sdelta + (size_t)q * a.Kp, a.LAd, a.K, a.Kp, i, lane);
-                if (lane == 0) {
-                    a.dout[(size_t)(v0 + q) * a.Kp + i] = b.x;
-                    const VecDesc vd = a.vecs[v0 + q];
-                    if (jj[q] >= vd.mid + 1)  // F:242: only steps from the latch on are ever read back
-                        psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (jj[q] - vd.mid - 1)) * a.K + i, b.k);
+                for (int q = 0; q < QB; ++q) {
+                    const int p = r * QB + q;
+                    ptmp[p] = tmp[r][q], picol[p] = col_i[r];
+                    pcol[p] = a.hiT + (size_t)col_i[r] * a.Kp;
+                    pdelta[p] = sdelta + (size_t)q * a.Kp;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) pcm[p][c] = cm[r][q][c];
+                }
+            resolve_tile<P>(pcm, ptmp, pcol, pdelta, picol, a.LAd, a.K, a.Kp, lane, res);
+#pragma unroll
+            for (int r = 0; r < RI; ++r) {
+                if (ibase + r >= a.K) continue;  // warp-uniform: the clamped duplicate column
+#pragma unroll
+                for (int q = 0; q < QB; ++q) {
+                    if (v0 + q >= a.nact) continue;  // warp-uniform: padding vector of the last group
+                    const Best b = res[r * QB + q];
+                    if (lane == 0) {
+                        const int i = ibase + r;
+                        a.dout[(size_t)(v0 + q) * a.Kp + i] = b.x;
+                        const VecDesc vd = a.vecs[v0 + q];
+                        if (jj[q] >= vd.mid + 1)  // F:242: only steps from the latch on are ever read back
+                            psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (jj[q] - vd.mid - 1)) * a.K + i, b.k);
+                    }
                 }
             }
         }

@@ -21,7 +21,10 @@
 //   * Steps hand over through the delta vector itself ({value, step} words polled from L2, see
 //     delta_wait_load): no grid barrier, no atomics.
 //   F: = /root/reference/src/FLASH_Viterbi_multithread.c
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "flashv_internal.h"
 #include "tile_geom.h"
@@ -34,6 +37,7 @@ constexpr int CPW = 2;                // columns a consumer warp owns per round
 constexpr int NCONS = NCW * 32;       // consumer threads
 constexpr int NTHREADS = NCONS + 32;  // + producer warp
 constexpr int MAX_STAGES = 64;
+constexpr int TRACE_STEPS = 64, TRACE_PTS = 6;
 constexpr int CTRL_BYTES = 2 * MAX_STAGES * 8;  // full[], empty[]
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -126,6 +130,7 @@ struct PersistArgs {
     int psi16;
     int nstage;
     int l2_hint;
+    long long *trace;  // optional [TRACE_STEPS][grid][2 warps][TRACE_PTS] clock64 samples (FLASHV_TRACE_FILE), else null
 };
 
 // ---- step-to-step hand-over without a barrier ------------------------------------------------
@@ -358,7 +363,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
         const int j = a.L + s;
         const float *tmp_row = a.LBf + (size_t)__ldg(a.ob + j) * a.Kp;  // F:167
         const bool keep = j >= a.mid + 1;                                // F:242
+        const bool tracing = a.trace != nullptr && s <= TRACE_STEPS && lane == 0 && (warp == 0 || warp == NCW - 1);
+        long long *tr = tracing ? a.trace + ((((size_t)(s - 1) * G + b) * 2 + (warp == 0 ? 0 : 1)) * TRACE_PTS) : nullptr;
+        if (tracing) tr[0] = clock64();
         delta_wait_load(a, s, reinterpret_cast<float *>(sdelta4), tid);
+        if (tracing) tr[1] = clock64();
 
         for (int rho = 0; rho < nrounds; ++rho) {
             const int ncr = min(TILE_RW, ncols - rho * TILE_RW);
@@ -415,6 +424,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                 if (lane == 0) mbar_arrive(&empty[st]);
                 if (++st == a.nstage) st = 0, parity ^= 1;
             }
+            if (tracing) tr[2] = clock64();
             if (!have0) continue;  // warp-uniform
             const float *round_base = slab + (size_t)rho * TILE_RW * a.Kp;
             Pending q0, q1;
@@ -423,6 +433,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             if (have1) scan_fetch(s1, cm1, round_base, ncr, rr1, a.K, a.Kp, lane);
             scan_commit(q0, s0, cm0, tmp0, round_base, ncr, rr0, sdelta, a.LAd, a.K, a.Kp, i0, lane);
             if (have1) scan_commit(q1, s1, cm1, tmp1, round_base, ncr, rr1, sdelta, a.LAd, a.K, a.Kp, i1, lane);
+            if (tracing) tr[3] = clock64();
             const Best r0 = pending_finish(q0);
             if (lane == 0) {
                 publish_delta(xout, i0, r0.x, s);
@@ -438,7 +449,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                 }
             }
         }
+        if (tracing) tr[4] = clock64();
         named_bar_sync(1, NCONS);  // sdelta is overwritten by the next step's load
+        if (tracing) tr[5] = clock64();
     }
 }
 
@@ -479,10 +492,31 @@ static int launch_persist(flashv_model *m, PersistArgs &a)
         return FLASHV_ERR_CUDA;
     }
     FV_CUDA(cudaMemsetAsync(a.xch, 0, (size_t)2 * a.Kp * sizeof(unsigned long long), ctx->stream));
+    // developer aid: FLASHV_TRACE_FILE=<path> dumps per-step phase timestamps of the last launch
+    const char *trace_path = a.nsteps >= TRACE_STEPS ? getenv("FLASHV_TRACE_FILE") : nullptr;
+    static long long *d_trace = nullptr;
+    const size_t trace_n = (size_t)TRACE_STEPS * m->tile_G * 2 * TRACE_PTS;
+    a.trace = nullptr;
+    if (trace_path) {
+        if (!d_trace) FV_CUDA(cudaMalloc(&d_trace, trace_n * sizeof(long long)));
+        FV_CUDA(cudaMemsetAsync(d_trace, 0, trace_n * sizeof(long long), ctx->stream));
+        a.trace = d_trace;
+    }
     void *params[] = {(void *)&a};
     // cooperative launch: every CTA polls data the others produce, so all must be co-resident;
     // the grid is the one the tiled table was laid out for
     FV_CUDA(cudaLaunchCooperativeKernel(fn, dim3(m->tile_G), dim3(NTHREADS), params, smem, ctx->stream));
+    if (trace_path) {
+        std::vector<long long> h(trace_n);
+        FV_CUDA(cudaMemcpyAsync(h.data(), d_trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        FV_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (FILE *fp = fopen(trace_path, "wb")) {
+            const int hdr[4] = {TRACE_STEPS, m->tile_G, 2, TRACE_PTS};
+            fwrite(hdr, sizeof(hdr), 1, fp);
+            fwrite(h.data(), sizeof(long long), trace_n, fp);
+            fclose(fp);
+        }
+    }
     return FLASHV_OK;
 }
 

@@ -120,4 +120,86 @@ __device__ __forceinline__ Best resolve_column(const float (&chain_max)[4], floa
     return b;
 }
 
+// Exact resolution of P (column, vector) pairs at once, executed by a full warp.  The latency of a
+// resolution is two dependent memory round trips (the winning chain's estimates from L2, then the
+// candidate's double from HBM); doing the pairs one after the other would pay them P times, so the
+// three phases below each run over all pairs before the next one starts:
+//   1. per pair: largest estimate, window threshold, the (first) chain inside the window; every
+//      lane loads its element of that chain
+//   2. per pair: the candidate (the common case is exactly one in the whole warp) loads its double
+//   3. per pair: exact value on the candidate lane, broadcast; anything unusual (several chains or
+//      several candidates inside the window, chains longer than a warp) falls back to
+//      resolve_column()
+// cm[p] are the lane's chain maxima of pair p, col[p] its hiT column, delta[p] its delta vector
+// (shared memory), out[p] receives (delta', psi) on every lane.
+template <int P>
+__device__ __forceinline__ void resolve_tile(const float (&cm)[P][4], const float (&tmp)[P], const float *const (&col)[P],
+                                             const float *const (&delta)[P], const int (&icol)[P],
+                                             const double *__restrict__ LAd, int K, int Kp, int lane, Best (&out)[P])
+{
+    const int chain_len = Kp >> 7;
+    float h[P];
+    int thr[P], kk[P];
+    unsigned slow = 0;  // bit p: pair p needs the general path (warp-uniform)
+    unsigned dead = 0;  // bit p: no finite estimate
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const float top = warp_max(fmaxf(fmaxf(cm[p][0], cm[p][1]), fmaxf(cm[p][2], cm[p][3])));
+        thr[p] = ford(top) - WINDOW_STEPS;
+        h[p] = 0.f, kk[p] = -1;
+        if (!(top > -FLT_MAX)) {
+            dead |= 1u << p;
+            continue;
+        }
+        int nchain = 0, w = 0, c = 0;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const unsigned hit = __ballot_sync(FULL_MASK, ford(cm[p][cc]) >= thr[p]);
+            if (hit && nchain == 0) w = __ffs(hit) - 1, c = cc;
+            nchain += __popc(hit);
+        }
+        if (nchain != 1 || chain_len > 32) {
+            slow |= 1u << p;
+            continue;
+        }
+        const int k = 4 * (w + 32 * lane) + c;
+        if (lane < chain_len && k < K) kk[p] = k, h[p] = __ldg(col[p] + k);
+    }
+    float pre[P];
+    double la[P];
+    int cand_lane[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        pre[p] = 0.f, la[p] = 0.0, cand_lane[p] = -1;
+        if ((slow | dead) >> p & 1u) continue;
+        bool in = false;
+        if (kk[p] >= 0) {
+            pre[p] = __fadd_rn(tmp[p], delta[p][kk[p]]);
+            in = ford(__fadd_rn(pre[p], h[p])) >= thr[p];
+        }
+        const unsigned cands = __ballot_sync(FULL_MASK, in);
+        if (__popc(cands) != 1) {
+            slow |= 1u << p;
+            continue;
+        }
+        cand_lane[p] = __ffs(cands) - 1;
+        if (in) la[p] = __ldg(LAd + (size_t)kk[p] * K + icol[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        if (dead >> p & 1u) {
+            out[p] = Best{-FLT_MAX, -1};
+        } else if (slow >> p & 1u) {
+            out[p] = resolve_column(cm[p], tmp[p], col[p], delta[p], LAd, K, Kp, icol[p], lane);
+        } else {
+            const float x = exact_cand(pre[p], la[p]);  // meaningful on the candidate lane only
+            Best b;
+            b.x = __shfl_sync(FULL_MASK, x, cand_lane[p]);
+            b.k = __shfl_sync(FULL_MASK, kk[p], cand_lane[p]);
+            if (!(b.x > -FLT_MAX)) b.x = -FLT_MAX, b.k = -1;
+            out[p] = b;
+        }
+    }
+}
+
 }  // namespace flashv
