@@ -215,7 +215,7 @@ extern "C" int flashv_plan_create(flashv_model *m, int T, int N, int batch, int 
         max_rows = std::max(max_rows, ps.psi_rows);
     }
     const int K = m->K, Kp = m->Kp;
-    const size_t psi_bytes = (size_t)max_rows * K * (p->psi16 ? 2 : 4);
+    const size_t psi_bytes = (size_t)max_rows * K * (p->psi16 ? 2 : 4) + 64;  // + slack: the staged backtrack reads whole 16-byte words
     const size_t delta_bytes = (size_t)(2 * p->max_vec + 4) * Kp * sizeof(float);  // two delta sets + the persistent engine's {value,step} exchange buffers
     std::vector<uint8_t> ismid((size_t)T, 0);
     for (int mid : p->sched.mids) ismid[mid] = 1;

@@ -101,59 +101,81 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
                 cm[r][q][0] = cm[r][q][1] = cm[r][q][2] = cm[r][q][3] = -INFINITY;
             }
         }
-        constexpr int UNROLL = QB * RI >= 8 ? 2 : (QB * RI >= 2 ? 4 : 8);
-#pragma unroll UNROLL
-        for (int t = lane; t < Kp4; t += 32) {
-            float4 h[RI];
+        // The hi values come straight from L2 (~1 us under load).  Small tiles hide that with many
+        // loads in flight per lane (deep unrolling); the big batched tile has no registers to spare
+        // for that, so it runs an explicit two-iterations-ahead prefetch instead.
+        if (QB * RI >= 8) {
+            float4 h1[RI], h2[RI];
 #pragma unroll
-            for (int r = 0; r < RI; ++r) h[r] = __ldg(col4[r] + t);
-#pragma unroll
-            for (int q = 0; q < QB; ++q) {
-                const float4 d = sdelta4[q * Kp4 + t];
+            for (int r = 0; r < RI; ++r) {
+                h1[r] = __ldg(col4[r] + lane);
+                h2[r] = lane + 32 < Kp4 ? __ldg(col4[r] + lane + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            for (int t = lane; t < Kp4; t += 32) {
+                float4 h[RI];
 #pragma unroll
                 for (int r = 0; r < RI; ++r) {
-                    cm[r][q][0] = fmaxf(cm[r][q][0], __fadd_rn(__fadd_rn(tmp[r][q], d.x), h[r].x));
-                    cm[r][q][1] = fmaxf(cm[r][q][1], __fadd_rn(__fadd_rn(tmp[r][q], d.y), h[r].y));
-                    cm[r][q][2] = fmaxf(cm[r][q][2], __fadd_rn(__fadd_rn(tmp[r][q], d.z), h[r].z));
-                    cm[r][q][3] = fmaxf(cm[r][q][3], __fadd_rn(__fadd_rn(tmp[r][q], d.w), h[r].w));
+                    h[r] = h1[r], h1[r] = h2[r];
+                    if (t + 64 < Kp4) h2[r] = __ldg(col4[r] + t + 64);
+                }
+#pragma unroll
+                for (int q = 0; q < QB; ++q) {
+                    const float4 d = sdelta4[q * Kp4 + t];
+#pragma unroll
+                    for (int r = 0; r < RI; ++r) {
+                        cm[r][q][0] = fmaxf(cm[r][q][0], __fadd_rn(__fadd_rn(tmp[r][q], d.x), h[r].x));
+                        cm[r][q][1] = fmaxf(cm[r][q][1], __fadd_rn(__fadd_rn(tmp[r][q], d.y), h[r].y));
+                        cm[r][q][2] = fmaxf(cm[r][q][2], __fadd_rn(__fadd_rn(tmp[r][q], d.z), h[r].z));
+                        cm[r][q][3] = fmaxf(cm[r][q][3], __fadd_rn(__fadd_rn(tmp[r][q], d.w), h[r].w));
+                    }
+                }
+            }
+        } else {
+            constexpr int UNROLL = QB * RI >= 2 ? 4 : 8;
+#pragma unroll UNROLL
+            for (int t = lane; t < Kp4; t += 32) {
+                float4 h[RI];
+#pragma unroll
+                for (int r = 0; r < RI; ++r) h[r] = __ldg(col4[r] + t);
+#pragma unroll
+                for (int q = 0; q < QB; ++q) {
+                    const float4 d = sdelta4[q * Kp4 + t];
+#pragma unroll
+                    for (int r = 0; r < RI; ++r) {
+                        cm[r][q][0] = fmaxf(cm[r][q][0], __fadd_rn(__fadd_rn(tmp[r][q], d.x), h[r].x));
+                        cm[r][q][1] = fmaxf(cm[r][q][1], __fadd_rn(__fadd_rn(tmp[r][q], d.y), h[r].y));
+                        cm[r][q][2] = fmaxf(cm[r][q][2], __fadd_rn(__fadd_rn(tmp[r][q], d.z), h[r].z));
+                        cm[r][q][3] = fmaxf(cm[r][q][3], __fadd_rn(__fadd_rn(tmp[r][q], d.w), h[r].w));
+                    }
                 }
             }
         }
-        // exact (value, first index) of the RI x QB pairs, their memory round trips overlapped
-        {
-            constexpr int P = RI * QB;
-            float ptmp[P];
-            const float *pcol[P];
-            const float *pdelta[P];
-            int picol[P];
-            float pcm[P][4];
-            Best res[P];
+        // exact (value, first index) of the pairs, one column (QB pairs) at a time so that the
+        // in-flight state of resolve_tile stays in registers; within a column the memory round
+        // trips of all QB pairs overlap
 #pragma unroll
-            for (int r = 0; r < RI; ++r)
+        for (int r = 0; r < RI; ++r) {
+            if (ibase + r >= a.K) continue;  // warp-uniform: the clamped duplicate column
+            const int i = ibase + r;
+            const float *pcol[QB];
+            const float *pdelta[QB];
+            int picol[QB];
+            Best res[QB];
 #pragma unroll
-                for (int q = 0; q < QB; ++q) {
-                    const int p = r * QB + q;
-                    ptmp[p] = tmp[r][q], picol[p] = col_i[r];
-                    pcol[p] = a.hiT + (size_t)col_i[r] * a.Kp;
-                    pdelta[p] = sdelta + (size_t)q * a.Kp;
+            for (int q = 0; q < QB; ++q) {
+                picol[q] = i;
+                pcol[q] = a.hiT + (size_t)i * a.Kp;
+                pdelta[q] = sdelta + (size_t)q * a.Kp;
+            }
+            resolve_tile<QB>(cm[r], tmp[r], pcol, pdelta, picol, a.LAd, a.K, a.Kp, lane, res);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) pcm[p][c] = cm[r][q][c];
-                }
-            resolve_tile<P>(pcm, ptmp, pcol, pdelta, picol, a.LAd, a.K, a.Kp, lane, res);
-#pragma unroll
-            for (int r = 0; r < RI; ++r) {
-                if (ibase + r >= a.K) continue;  // warp-uniform: the clamped duplicate column
-#pragma unroll
-                for (int q = 0; q < QB; ++q) {
-                    if (v0 + q >= a.nact) continue;  // warp-uniform: padding vector of the last group
-                    const Best b = res[r * QB + q];
-                    if (lane == 0) {
-                        const int i = ibase + r;
-                        a.dout[(size_t)(v0 + q) * a.Kp + i] = b.x;
-                        const VecDesc vd = a.vecs[v0 + q];
-                        if (jj[q] >= vd.mid + 1)  // F:242: only steps from the latch on are ever read back
-                            psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (jj[q] - vd.mid - 1)) * a.K + i, b.k);
-                    }
+            for (int q = 0; q < QB; ++q) {
+                if (v0 + q >= a.nact) continue;  // warp-uniform: padding vector of the last group
+                if (lane == 0) {
+                    a.dout[(size_t)(v0 + q) * a.Kp + i] = res[q].x;
+                    const VecDesc vd = a.vecs[v0 + q];
+                    if (jj[q] >= vd.mid + 1)  // F:242: only steps from the latch on are ever read back
+                        psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (jj[q] - vd.mid - 1)) * a.K + i, res[q].k);
                 }
             }
         }
@@ -212,6 +234,45 @@ __global__ void k_flash_backtrack(const VecDesc *__restrict__ vecs, int nvec, co
         if ((vd.flags & VEC_FIRST_PASS) && ismid[j - 1]) out[j - 1] = state;
     }
     if (!(vd.flags & VEC_FIRST_PASS)) out[vd.mid] = state;
+}
+
+// The same walk for ONE long vector (the first pass: T-1-mids[0] dependent hops).  A hop through
+// global memory costs an L2 round trip (~0.5 us: 125 us for T=256); here the CTA copies a window
+// of consecutive rows into shared memory with coalesced 16-byte loads and thread 0 hops inside it.
+__global__ void __launch_bounds__(512) k_flash_backtrack_staged(const VecDesc *__restrict__ vecs, const void *__restrict__ psi,
+                                                                int psi16, int K, int T, const uint8_t *__restrict__ ismid,
+                                                                const int32_t *__restrict__ endstate,
+                                                                int32_t *__restrict__ ans, int win_rows)
+{
+    extern __shared__ uint4 swin[];
+    __shared__ int s_state;
+    const VecDesc vd = vecs[0];
+    const size_t esz = psi16 ? 2 : 4;
+    const size_t row_bytes = (size_t)K * esz;
+    int32_t *out = ans + (size_t)vd.seq * T;
+    if (threadIdx.x == 0) s_state = endstate[0];
+    for (int jhi = vd.R; jhi >= vd.mid + 1; jhi -= win_rows) {
+        const int jlo = max(jhi - win_rows + 1, vd.mid + 1);
+        const size_t lo = (size_t)(vd.psi_row + (jlo - vd.mid - 1)) * row_bytes;      // first byte of row jlo
+        const size_t hi = (size_t)(vd.psi_row + (jhi - vd.mid - 1) + 1) * row_bytes;  // one past row jhi
+        const size_t lo16 = lo & ~(size_t)15;
+        const int n16 = (int)((hi - lo16 + 15) >> 4);
+        const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(psi) + lo16);
+        __syncthreads();  // previous window fully consumed
+        for (int t = threadIdx.x; t < n16; t += blockDim.x) swin[t] = src[t];  // reads past `hi` stay inside the store's padding
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned char *base = reinterpret_cast<const unsigned char *>(swin) + (lo - lo16);
+            int state = s_state;
+            for (int j = jhi; j >= jlo; --j) {
+                if (state >= 0) state = psi_load(base, psi16, (size_t)(j - jlo) * K + state);
+                if ((vd.flags & VEC_FIRST_PASS) && ismid[j - 1]) out[j - 1] = state;
+            }
+            s_state = state;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && !(vd.flags & VEC_FIRST_PASS)) out[vd.mid] = s_state;
 }
 
 // ---- host orchestration -------------------------------------------------------------------------
@@ -288,8 +349,17 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
     // Only full-range vectors read delta here, and they run all max_steps steps of the pass.
     k_flash_end<<<pass.nvec, 256, 0, st>>>(vecs, pass.nvec, final_delta, K, Kp, T, p->d_ans, p->d_score, p->d_endstate);
     FV_CUDA(cudaGetLastError());
-    k_flash_backtrack<<<(pass.nvec + 127) / 128, 128, 0, st>>>(vecs, pass.nvec, p->d_psi, p->psi16, K, T, p->d_ismid,
-                                                               p->d_endstate, p->d_ans);
+    const size_t row_bytes = (size_t)K * (p->psi16 ? 2 : 4);
+    const int win_rows = (int)((200 * 1024 - 32) / row_bytes);
+    if (pass.nvec == 1 && pass.max_steps >= 16 && win_rows >= 4) {
+        const size_t smem = (size_t)win_rows * row_bytes + 32;
+        FV_CUDA(cudaFuncSetAttribute(k_flash_backtrack_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        k_flash_backtrack_staged<<<1, 512, smem, st>>>(vecs, p->d_psi, p->psi16, K, T, p->d_ismid, p->d_endstate, p->d_ans,
+                                                      win_rows);
+    } else {
+        k_flash_backtrack<<<(pass.nvec + 127) / 128, 128, 0, st>>>(vecs, pass.nvec, p->d_psi, p->psi16, K, T, p->d_ismid,
+                                                                   p->d_endstate, p->d_ans);
+    }
     FV_CUDA(cudaGetLastError());
     p->launches += 2;
     return FLASHV_OK;
