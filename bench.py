@@ -202,12 +202,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    import shard
+
     def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.max_over_ranks(x, dist, dev)
 
     A, B, Pi, ob, raw = synthetic(rank)
     stream = torch.cuda.Stream(device=dev)
@@ -258,6 +256,27 @@ def run_ours(args):
     barrier()
     e2e_value = world * K * K * T * args.steps / e2e_s / 1e9
 
+    # the same decode at the reference-comparable segment counts, for the record (3 runs each)
+    also = {}
+    for n_other in (8, 64):
+        if n_other == args.segments:
+            continue
+        p2 = fv.Plan(model, T, n_other, 1, 0, engine)
+        p2.upload_ptr(ob_pinned.data_ptr())
+        p2.run()
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(3):
+                p2.run()
+            e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        also[f"N={n_other}"] = {"ms_per_decode": ms, "value": K * K * T / (ms * 1e-3) / 1e9,
+                                "executed_steps": p2.report().executed_steps}
+        p2.close()
+
     rep = plan.report()
     peak, peak_src = peaks()
     fp_mean = sum(fp_ms) / len(fp_ms)
@@ -288,6 +307,7 @@ def run_ours(args):
                      "traffic": traffic, "peak_source": peak_src, "ms_per_launch": fp_mean,
                      "algorithmic_bytes_per_launch": algo_bytes},
         "model_prep_ms": model.prep_ms,
+        "other_segment_counts": also,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -324,7 +344,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--segments", type=int, default=64, help="MAX_THREADS of the reference = segment count N")
+    ap.add_argument("--segments", type=int, default=127,
+                    help="MAX_THREADS of the reference = segment count N (127 is the largest the reference handles at T=256: "
+                         "T == 2N is broken there); N=8 and N=64 are timed beside it")
     ap.add_argument("--engine", default="auto", choices=["auto", "step", "persistent"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the parity check and the CPU baseline leg")
     args = ap.parse_args()

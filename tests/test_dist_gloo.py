@@ -1,0 +1,57 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: sequences shard b mod G, no data-path
+collective, paths gathered on rank 0, times reduced with MAX.  The per-rank decode is played by the
+oracle here (this is a CPU test of the plumbing); on the GPU box the same functions wrap
+flashv_decode_batch (bench.py --gpus N)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_golden
+
+sys.path.insert(0, str(ROOT / "flash-viterbi_b200" / "host"))
+
+
+def _worker(rank, world, port, obs, N, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import shard
+        from oracle import oracle
+
+        g = load_golden("hmm_k37")
+        om = oracle.OracleModel(g["A"], g["B"], g["Pi"])
+        mine = shard.rank_sequences(len(obs), world, rank)
+        local = np.stack([om.flash(obs[b], N)[0] for b in mine]) if len(mine) else np.zeros((0, obs.shape[1]), np.int32)
+        slowest = shard.max_over_ranks(1.0 + rank, dist)
+        full = shard.gather_paths(local, len(obs), dist)
+        if rank == 0:
+            ret["paths"] = full
+            ret["slowest"] = slowest
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sequences_shard_over_two_ranks():
+    import shard
+
+    assert list(shard.rank_sequences(7, 2, 0)) == [0, 2, 4, 6] and list(shard.rank_sequences(7, 2, 1)) == [1, 3, 5]
+    assert sorted(np.concatenate([shard.rank_sequences(9, 4, r) for r in range(4)])) == list(range(9))
+    g = load_golden("hmm_k37")
+    rng = np.random.RandomState(5)
+    obs = rng.randint(0, g["B"].shape[1], (5, 40)).astype(np.int32)
+    from oracle import oracle
+
+    om = oracle.OracleModel(g["A"], g["B"], g["Pi"])
+    want = np.stack([om.flash(o, 3)[0] for o in obs])
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        port = 29500 + (os.getpid() % 2000)
+        mp.spawn(_worker, args=(2, port, obs, 3, ret), nprocs=2, join=True)
+        assert np.array_equal(ret["paths"], want)
+        assert ret["slowest"] == 2.0
