@@ -169,22 +169,44 @@ __device__ __forceinline__ void delta_wait_load(const PersistArgs &a, int s, flo
             sd2[t] = v;
         }
     } else {
+        // All of a thread's entries are requested before any is inspected, so a step pays one L2
+        // round trip here when the data is already there, not one per entry.
         const unsigned long long *x = a.xch + (size_t)((s - 1) & 1) * a.Kp;
         const unsigned want = (unsigned)(s - 1);
-        for (int t = ctid; t < Kp2; t += NCONS) {
-            float2 v = make_float2(0.f, 0.f);
-            const int k = 2 * t;
-            if (k < a.K) {
-                unsigned long long w0, w1, t0 = 0;
-                for (uint32_t spins = 0;; ++spins) {
-                    ld_volatile_2x64(x + k, w0, w1);
-                    if ((unsigned)(w0 >> 32) == want && (k + 1 >= a.K || (unsigned)(w1 >> 32) == want)) break;
-                    watchdog(spins * 64u + 63u, t0);
-                }
-                v.x = __uint_as_float((unsigned)w0);
-                if (k + 1 < a.K) v.y = __uint_as_float((unsigned)w1);
+        constexpr int NB = 8;  // entries (pairs of delta values) in flight per thread
+        for (int t0 = ctid; t0 < Kp2; t0 += NCONS * NB) {
+            unsigned long long w0[NB], w1[NB];
+            unsigned pending = 0;
+#pragma unroll
+            for (int e = 0; e < NB; ++e) {
+                const int t = t0 + e * NCONS;
+                if (t < Kp2 && 2 * t < a.K) pending |= 1u << e;
             }
-            sd2[t] = v;
+            unsigned long long tw = 0;
+            for (uint32_t spins = 0; pending; ++spins) {
+#pragma unroll
+                for (int e = 0; e < NB; ++e)
+                    if (pending >> e & 1u) ld_volatile_2x64(x + 2 * (t0 + e * NCONS), w0[e], w1[e]);
+#pragma unroll
+                for (int e = 0; e < NB; ++e)
+                    if (pending >> e & 1u) {
+                        const int k = 2 * (t0 + e * NCONS);
+                        if ((unsigned)(w0[e] >> 32) == want && (k + 1 >= a.K || (unsigned)(w1[e] >> 32) == want))
+                            pending &= ~(1u << e);
+                    }
+                if (pending) watchdog(spins * 64u + 63u, tw);
+            }
+#pragma unroll
+            for (int e = 0; e < NB; ++e) {
+                const int t = t0 + e * NCONS;
+                if (t < Kp2) {
+                    const int k = 2 * t;
+                    float2 v = make_float2(0.f, 0.f);  // padding lanes stay finite (the table pads with -inf)
+                    if (k < a.K) v.x = __uint_as_float((unsigned)w0[e]);
+                    if (k + 1 < a.K) v.y = __uint_as_float((unsigned)w1[e]);
+                    sd2[t] = v;
+                }
+            }
         }
     }
     named_bar_sync(1, NCONS);

@@ -19,3 +19,8 @@ for c in; do
 FLASHV_CHUNK=$c timeout 120 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_persistent_chunk$c.log 2>&1
 done
 tail -2 gpurun_out/smoke.log; tail -1 gpurun_out/bench_persistent_n64.log
+python tools/profile_target.py --beam 128 --segments 8 --iters 2 > gpurun_out/bs_n8_b128.log 2>&1
+python tools/profile_target.py --beam 128 --segments 1 --iters 2 >> gpurun_out/bs_n8_b128.log 2>&1
+python tools/profile_target.py --beam 32 --segments 8 --iters 2 >> gpurun_out/bs_n8_b128.log 2>&1
+cat gpurun_out/bs_n8_b128.log
+bash tools/gpu_trace.sh
