@@ -131,9 +131,22 @@ __global__ void __launch_bounds__(1024) k_bs_pass(const BsArgs a)
             const float tmp = __ldg(a.LBf + (size_t)o * a.Kp + i);  // S:439
             float best = -FLT_MAX;
             int arg = -1;
-            for (int c = 0; c < B; ++c) {  // S:440-446, slots in array order, strict '>'
-                const float pre = __fadd_rn(tmp, hv[c]);
-                const float x = exact_cand(pre, __ldg(a.LAd + (size_t)hs[c] * K + i));
+            // S:440-446, slots in array order, strict '>'.  The row reads are independent of the
+            // running maximum: fetch a batch of them before the compare chain consumes any.
+            constexpr int UB = 8;
+            int c = 0;
+            for (; c + UB <= B; c += UB) {
+                double la[UB];
+#pragma unroll
+                for (int e = 0; e < UB; ++e) la[e] = __ldg(a.LAd + (size_t)hs[c + e] * K + i);
+#pragma unroll
+                for (int e = 0; e < UB; ++e) {
+                    const float x = exact_cand(__fadd_rn(tmp, hv[c + e]), la[e]);
+                    if (x > best) best = x, arg = c + e;
+                }
+            }
+            for (; c < B; ++c) {
+                const float x = exact_cand(__fadd_rn(tmp, hv[c]), __ldg(a.LAd + (size_t)hs[c] * K + i));
                 if (x > best) best = x, arg = c;
             }
             sscore[i] = best;

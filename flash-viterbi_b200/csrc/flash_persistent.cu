@@ -278,10 +278,14 @@ __device__ __forceinline__ void scan_fetch(Scan &sc, const float (&cm)[4], const
                 continue;
             }
             const int k = 4 * (w + 32 * lane) + c;  // element `lane` of chain (w, c)
-            if (lane < chain_len && k < K) {
-                const float h = __ldg(round_base + tile_round_off(Kp, ncr, rr, k));
-                if (used == 0) sc.hi0 = h, sc.k0 = k;
-                else sc.hi1 = h, sc.k1 = k;
+            // `used` is warp-uniform: branch, so that the load lands in its slot without being
+            // consumed (a select on the loaded value would wait for it right here)
+            const bool mine = lane < chain_len && k < K;
+            const float *src = round_base + tile_round_off(Kp, ncr, rr, mine ? k : 0);
+            if (used == 0) {
+                if (mine) sc.k0 = k, sc.hi0 = __ldg(src);
+            } else {
+                if (mine) sc.k1 = k, sc.hi1 = __ldg(src);
             }
             ++used;
         }
