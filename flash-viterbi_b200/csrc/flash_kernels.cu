@@ -30,6 +30,54 @@ __global__ void k_flash_init(const VecDesc *__restrict__ vecs, int nvec, const i
     }
 }
 
+// Running maxima of the float estimate for an RI x QB tile (RI destination columns, QB delta
+// vectors in shared memory) over all source states: lane l owns k = 4*(l+32u)+c.  The hi values
+// come straight from L2 (~1 us under load): small tiles hide that with many loads in flight per
+// lane (deep unrolling); the big batched tile has no registers to spare for that and runs an
+// explicit two-iterations-ahead register prefetch instead.
+template <int QB, int RI>
+__device__ __forceinline__ void tile_accumulate(float (&cm)[RI][QB][4], const float (&tmp)[RI][QB],
+                                                const float4 *const (&col4)[RI], const float4 *sdelta4, int Kp4, int lane)
+{
+#define FV_ACC(H)                                                                                   \
+    _Pragma("unroll") for (int q = 0; q < QB; ++q) {                                                \
+        const float4 d = sdelta4[q * Kp4 + t];                                                       \
+        _Pragma("unroll") for (int r = 0; r < RI; ++r) {                                            \
+            cm[r][q][0] = fmaxf(cm[r][q][0], __fadd_rn(__fadd_rn(tmp[r][q], d.x), H[r].x));          \
+            cm[r][q][1] = fmaxf(cm[r][q][1], __fadd_rn(__fadd_rn(tmp[r][q], d.y), H[r].y));          \
+            cm[r][q][2] = fmaxf(cm[r][q][2], __fadd_rn(__fadd_rn(tmp[r][q], d.z), H[r].z));          \
+            cm[r][q][3] = fmaxf(cm[r][q][3], __fadd_rn(__fadd_rn(tmp[r][q], d.w), H[r].w));          \
+        }                                                                                            \
+    }
+    if (QB * RI >= 8) {
+        float4 h1[RI], h2[RI];
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+            h1[r] = __ldg(col4[r] + lane);
+            h2[r] = lane + 32 < Kp4 ? __ldg(col4[r] + lane + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int t = lane; t < Kp4; t += 32) {
+            float4 h[RI];
+#pragma unroll
+            for (int r = 0; r < RI; ++r) {
+                h[r] = h1[r], h1[r] = h2[r];
+                if (t + 64 < Kp4) h2[r] = __ldg(col4[r] + t + 64);
+            }
+            FV_ACC(h)
+        }
+    } else {
+        constexpr int UNROLL = QB * RI >= 2 ? 4 : 8;
+#pragma unroll UNROLL
+        for (int t = lane; t < Kp4; t += 32) {
+            float4 h[RI];
+#pragma unroll
+            for (int r = 0; r < RI; ++r) h[r] = __ldg(col4[r] + t);
+            FV_ACC(h)
+        }
+    }
+#undef FV_ACC
+}
+
 // ---- engine STEP: one launch per trellis step ------------------------------------------------
 // A block of NWARP warps keeps delta of QB vectors in shared memory and walks over tiles of
 // NWARP*RI destination columns (grid.x workers per vector group, grid.y vector groups).  A warp
@@ -101,55 +149,7 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
                 cm[r][q][0] = cm[r][q][1] = cm[r][q][2] = cm[r][q][3] = -INFINITY;
             }
         }
-        // The hi values come straight from L2 (~1 us under load).  Small tiles hide that with many
-        // loads in flight per lane (deep unrolling); the big batched tile has no registers to spare
-        // for that, so it runs an explicit two-iterations-ahead prefetch instead.
-        if (QB * RI >= 8) {
-            float4 h1[RI], h2[RI];
-#pragma unroll
-            for (int r = 0; r < RI; ++r) {
-                h1[r] = __ldg(col4[r] + lane);
-                h2[r] = lane + 32 < Kp4 ? __ldg(col4[r] + lane + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            for (int t = lane; t < Kp4; t += 32) {
-                float4 h[RI];
-#pragma unroll
-                for (int r = 0; r < RI; ++r) {
-                    h[r] = h1[r], h1[r] = h2[r];
-                    if (t + 64 < Kp4) h2[r] = __ldg(col4[r] + t + 64);
-                }
-#pragma unroll
-                for (int q = 0; q < QB; ++q) {
-                    const float4 d = sdelta4[q * Kp4 + t];
-#pragma unroll
-                    for (int r = 0; r < RI; ++r) {
-                        cm[r][q][0] = fmaxf(cm[r][q][0], __fadd_rn(__fadd_rn(tmp[r][q], d.x), h[r].x));
-                        cm[r][q][1] = fmaxf(cm[r][q][1], __fadd_rn(__fadd_rn(tmp[r][q], d.y), h[r].y));
-                        cm[r][q][2] = fmaxf(cm[r][q][2], __fadd_rn(__fadd_rn(tmp[r][q], d.z), h[r].z));
-                        cm[r][q][3] = fmaxf(cm[r][q][3], __fadd_rn(__fadd_rn(tmp[r][q], d.w), h[r].w));
-                    }
-                }
-            }
-        } else {
-            constexpr int UNROLL = QB * RI >= 2 ? 4 : 8;
-#pragma unroll UNROLL
-            for (int t = lane; t < Kp4; t += 32) {
-                float4 h[RI];
-#pragma unroll
-                for (int r = 0; r < RI; ++r) h[r] = __ldg(col4[r] + t);
-#pragma unroll
-                for (int q = 0; q < QB; ++q) {
-                    const float4 d = sdelta4[q * Kp4 + t];
-#pragma unroll
-                    for (int r = 0; r < RI; ++r) {
-                        cm[r][q][0] = fmaxf(cm[r][q][0], __fadd_rn(__fadd_rn(tmp[r][q], d.x), h[r].x));
-                        cm[r][q][1] = fmaxf(cm[r][q][1], __fadd_rn(__fadd_rn(tmp[r][q], d.y), h[r].y));
-                        cm[r][q][2] = fmaxf(cm[r][q][2], __fadd_rn(__fadd_rn(tmp[r][q], d.z), h[r].z));
-                        cm[r][q][3] = fmaxf(cm[r][q][3], __fadd_rn(__fadd_rn(tmp[r][q], d.w), h[r].w));
-                    }
-                }
-            }
-        }
+        tile_accumulate<QB, RI>(cm, tmp, col4, sdelta4, Kp4, lane);
         // exact (value, first index) of the pairs, one column (QB pairs) at a time so that the
         // in-flight state of resolve_tile stays in registers; within a column the memory round
         // trips of all QB pairs overlap
@@ -178,6 +178,127 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
                         psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (jj[q] - vd.mid - 1)) * a.K + i, res[q].k);
                 }
             }
+        }
+    }
+}
+
+// ---- many vectors over a small table: one CTA walks QB vectors through ALL their steps ------
+// For batches of sequences (BASELINE config 4: 8192 sequences, K=512) a launch per step would
+// re-stage delta through HBM every step.  Here delta of a group of QB vectors ping-pongs between
+// two shared-memory buffers for the whole pass, the CTA computes every destination column of
+// every step itself (warps take RI columns at a time), and only backpointer rows and the final
+// delta go to HBM.  No inter-CTA dependency at all: groups are independent units of work.
+struct GroupArgs {
+    const float *hiT;
+    const double *LAd, *LBd, *LPi;
+    const float *LBf;
+    int K, Kp;
+    const VecDesc *vecs;
+    int nvec;
+    const int32_t *ob;
+    const int32_t *ans;
+    int T;
+    float *dfinal;  // [nvec][Kp] delta after each vector's last step (full-range vectors read it)
+    void *psi;
+    int psi16;
+};
+
+template <int QB, int RI, int NWARP>
+__global__ void __launch_bounds__(NWARP * 32) k_flash_group_pass(const GroupArgs a)
+{
+    extern __shared__ float4 sgroup4[];  // [2][QB][Kp/4]
+    constexpr int NT = NWARP * 32;
+    const int Kp4 = a.Kp >> 2;
+    float *sbuf = reinterpret_cast<float *>(sgroup4);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ngroups = (a.nvec + QB - 1) / QB;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int v0 = g * QB;
+        VecDesc vd[QB];
+        int gsteps = 0;
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+            vd[q] = a.vecs[min(v0 + q, a.nvec - 1)];
+            if (v0 + q >= a.nvec) vd[q].R = vd[q].L;  // padding vector: no steps
+            gsteps = max(gsteps, vd[q].R - vd[q].L);
+        }
+        __syncthreads();  // previous group done with the buffers
+        // start vectors, F:142 / F:220
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+            const int32_t *ob = a.ob + (size_t)vd[q].seq * a.T;
+            const int prev = vd[q].L == 0 ? -1 : a.ans[(size_t)vd[q].seq * a.T + vd[q].L - 1];
+            const int o = ob[vd[q].L];
+            for (int i = tid; i < a.Kp; i += NT) {
+                float v = 0.f;  // padding lanes stay finite (hiT pads with -inf)
+                if (i < a.K) {
+                    const double head = prev < 0 ? a.LPi[i] : a.LAd[(size_t)prev * a.K + i];
+                    v = __double2float_rn(__dadd_rn(head, a.LBd[(size_t)o * a.K + i]));
+                }
+                sbuf[(size_t)q * a.Kp + i] = v;
+                sbuf[(size_t)(QB + q) * a.Kp + i] = 0.f;
+            }
+        }
+        __syncthreads();
+        int cur = 0;
+        for (int s = 1; s <= gsteps; ++s) {
+            const float *sin = sbuf + (size_t)cur * QB * a.Kp;
+            float *sout = sbuf + (size_t)(cur ^ 1) * QB * a.Kp;
+            const float4 *sin4 = reinterpret_cast<const float4 *>(sin);
+            const float *tmp_row[QB];
+            bool live[QB];
+#pragma unroll
+            for (int q = 0; q < QB; ++q) {
+                live[q] = s <= vd[q].R - vd[q].L;
+                const int j = min(vd[q].L + s, vd[q].R);
+                tmp_row[q] = a.LBf + (size_t)a.ob[(size_t)vd[q].seq * a.T + j] * a.Kp;  // F:167
+            }
+            for (int ibase = warp * RI; ibase < a.K; ibase += NWARP * RI) {
+                int col_i[RI];
+                const float4 *col4[RI];
+                float tmp[RI][QB];
+                float cm[RI][QB][4];
+#pragma unroll
+                for (int r = 0; r < RI; ++r) {
+                    col_i[r] = min(ibase + r, a.K - 1);
+                    col4[r] = reinterpret_cast<const float4 *>(a.hiT + (size_t)col_i[r] * a.Kp);
+#pragma unroll
+                    for (int q = 0; q < QB; ++q) {
+                        tmp[r][q] = __ldg(tmp_row[q] + col_i[r]);
+                        cm[r][q][0] = cm[r][q][1] = cm[r][q][2] = cm[r][q][3] = -INFINITY;
+                    }
+                }
+                tile_accumulate<QB, RI>(cm, tmp, col4, sin4, Kp4, lane);
+#pragma unroll
+                for (int r = 0; r < RI; ++r) {
+                    if (ibase + r >= a.K) continue;  // warp-uniform: the clamped duplicate column
+                    const int i = ibase + r;
+                    const float *pcol[QB];
+                    const float *pdelta[QB];
+                    int picol[QB];
+                    Best res[QB];
+#pragma unroll
+                    for (int q = 0; q < QB; ++q) {
+                        picol[q] = i;
+                        pcol[q] = a.hiT + (size_t)i * a.Kp;
+                        pdelta[q] = sin + (size_t)q * a.Kp;
+                    }
+                    resolve_tile<QB>(cm[r], tmp[r], pcol, pdelta, picol, a.LAd, a.K, a.Kp, lane, res);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int q = 0; q < QB; ++q) {
+                            if (!live[q]) continue;
+                            sout[(size_t)q * a.Kp + i] = res[q].x;
+                            const int j = vd[q].L + s;
+                            if (j >= vd[q].mid + 1)  // F:242
+                                psi_store(a.psi, a.psi16, (size_t)(vd[q].psi_row + (j - vd[q].mid - 1)) * a.K + i, res[q].k);
+                            if (j == vd[q].R) a.dfinal[(size_t)(v0 + q) * a.Kp + i] = res[q].x;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            cur ^= 1;
         }
     }
 }
@@ -328,7 +449,24 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
 
     const float *final_delta = d0;
     const bool persistent = p->engine == FLASHV_ENGINE_PERSISTENT && pass.nvec == 1;
-    if (persistent) {
+    // many vectors over a table small enough that two delta sets of 8 vectors fit in shared memory
+    const bool grouped = p->engine != FLASHV_ENGINE_STEP && pass.nvec >= 2 * ctx->sm_count &&
+                         (size_t)2 * 8 * Kp * sizeof(float) <= 160 * 1024;
+    if (grouped) {
+        GroupArgs g;
+        g.hiT = m->hiT, g.LAd = m->LAd, g.LBd = m->LBd, g.LPi = m->LPi, g.LBf = m->LBf, g.K = K, g.Kp = Kp;
+        g.vecs = vecs, g.nvec = pass.nvec, g.ob = p->d_ob, g.ans = p->d_ans, g.T = T;
+        g.dfinal = d1, g.psi = p->d_psi, g.psi16 = p->psi16;
+        const size_t smem = (size_t)2 * 8 * Kp * sizeof(float);
+        FV_CUDA(cudaFuncSetAttribute(k_flash_group_pass<8, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int grid = ctx->sm_count;  // 512 threads x 128 registers: one CTA per SM, looping over groups
+        const int ngroups = (pass.nvec + 7) / 8;
+        if (grid > ngroups) grid = ngroups;
+        k_flash_group_pass<8, 2, 16><<<grid, 512, smem, st>>>(g);
+        FV_CUDA(cudaGetLastError());
+        ++p->launches;
+        final_delta = d1;
+    } else if (persistent) {
         int rc = persistent_pass(p, pass);
         if (rc != FLASHV_OK) return rc;
         final_delta = d1;  // the persistent kernel leaves the last delta there

@@ -181,6 +181,51 @@ def test_batch_equals_single(fv, oracle_mod, gpu_ctx):
     model.close()
 
 
+def test_large_batch_group_engine(fv, oracle_mod, gpu_ctx):
+    """Batches big enough for the group-persistent kernel (one CTA walks 8 vectors through all
+    their steps); every sequence must equal its single decode by the oracle."""
+    K, M, T = 96, 8, 24
+    A, B, Pi = random_hmm(K, M, 0.3, 61)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    rng = np.random.RandomState(61)
+    obs = rng.randint(0, M, (333, T)).astype(np.int32)
+    for N in (3, 1):
+        paths, scores, rep = model.decode_batch(obs, N)
+        for b in range(obs.shape[0]):
+            want, wscore, _ = om.flash(obs[b], N)
+            assert np.array_equal(paths[b], want), (N, b)
+            assert _bits(scores[b]) == _bits(wscore)
+    model.close()
+
+
+def test_wide_model_multi_round(fv, oracle_mod, gpu_ctx):
+    """K large enough that a persistent CTA owns more columns than one round (28) and a chain is
+    longer than a warp (K > 4096): the general paths of the window scan."""
+    K, M, T = 8200, 3, 6
+    A, B, Pi = random_hmm(K, M, 0.004, 71)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    rng = np.random.RandomState(71)
+    d = om.init(-1, 0)
+    for it in range(2):
+        o = int(rng.randint(M))
+        want_d, want_psi = om.step(d, o)
+        for eng in (fv.ENGINE_STEP, fv.ENGINE_PERSISTENT):
+            got_d, got_psi = model.trellis_step(d, o, eng)
+            assert np.array_equal(got_psi, want_psi), (it, eng)
+            assert np.array_equal(_bits(got_d), _bits(want_d)), (it, eng)
+        d = want_d
+    ob = rng.randint(0, M, T).astype(np.int32)
+    for N in (1, 2):
+        want, wscore, _ = om.flash(ob, N)
+        if not wscore > NEG_MAX:
+            continue
+        got, score, rep = model.decode(ob, N)
+        assert np.array_equal(got, want) and _bits(score) == _bits(wscore)
+    model.close()
+
+
 def test_error_behaviour(fv, gpu_ctx):
     A, B, Pi = random_hmm(16, 4, 0.5, 51)
     model = fv.Model(gpu_ctx, A, B, Pi)
