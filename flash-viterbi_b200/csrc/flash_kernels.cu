@@ -19,14 +19,14 @@ __global__ void k_flash_init(const VecDesc *__restrict__ vecs, int nvec, const i
                              const double *__restrict__ LBd, const double *__restrict__ LPi, int K, int Kp,
                              float *__restrict__ delta)
 {
-    const int v = blockIdx.y;
-    if (v >= nvec) return;
-    const VecDesc vd = vecs[v];
-    const int prev = vd.L == 0 ? -1 : ans[(size_t)vd.seq * T + vd.L - 1];
-    const int o = ob[(size_t)vd.seq * T + vd.L];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
-        const double head = prev < 0 ? LPi[i] : LAd[(size_t)prev * K + i];
-        delta[(size_t)v * Kp + i] = __double2float_rn(__dadd_rn(head, LBd[(size_t)o * K + i]));
+    for (int v = blockIdx.y; v < nvec; v += gridDim.y) {
+        const VecDesc vd = vecs[v];
+        const int prev = vd.L == 0 ? -1 : ans[(size_t)vd.seq * T + vd.L - 1];
+        const int o = ob[(size_t)vd.seq * T + vd.L];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
+            const double head = prev < 0 ? LPi[i] : LAd[(size_t)prev * K + i];
+            delta[(size_t)v * Kp + i] = __double2float_rn(__dadd_rn(head, LBd[(size_t)o * K + i]));
+        }
     }
 }
 
@@ -442,16 +442,17 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
     float *d0 = p->d_delta, *d1 = p->d_delta + (size_t)p->max_vec * Kp;
 
     if (time_it) FV_CUDA(cudaEventRecord(ctx->ev[2], st));
-    dim3 ig((K + 255) / 256, pass.nvec);
-    k_flash_init<<<ig, 256, 0, st>>>(vecs, pass.nvec, p->d_ob, p->d_ans, T, m->LAd, m->LBd, m->LPi, K, Kp, d0);
-    FV_CUDA(cudaGetLastError());
-    ++p->launches;
-
     const float *final_delta = d0;
     const bool persistent = p->engine == FLASHV_ENGINE_PERSISTENT && pass.nvec == 1;
     // many vectors over a table small enough that two delta sets of 8 vectors fit in shared memory
     const bool grouped = p->engine != FLASHV_ENGINE_STEP && pass.nvec >= 2 * ctx->sm_count &&
                          (size_t)2 * 8 * Kp * sizeof(float) <= 160 * 1024;
+    if (!grouped) {  // the group kernel builds its start vectors itself
+        dim3 ig((K + 255) / 256, pass.nvec < 65535 ? pass.nvec : 65535);
+        k_flash_init<<<ig, 256, 0, st>>>(vecs, pass.nvec, p->d_ob, p->d_ans, T, m->LAd, m->LBd, m->LPi, K, Kp, d0);
+        FV_CUDA(cudaGetLastError());
+        ++p->launches;
+    }
     if (grouped) {
         GroupArgs g;
         g.hiT = m->hiT, g.LAd = m->LAd, g.LBd = m->LBd, g.LPi = m->LPi, g.LBf = m->LBf, g.K = K, g.Kp = Kp;
