@@ -203,32 +203,49 @@ struct GroupArgs {
     int psi16;
 };
 
+// Per step the CTA works in two phases separated by a barrier:
+//   A  warps sweep the columns (RI at a time) and keep only the running maxima of the estimates;
+//      per (column, vector) pair they leave a 8-byte record: the largest estimate and the one
+//      chain (lane, component) whose maximum lies inside the window (or "ambiguous");
+//   B  one THREAD per pair re-reads that chain (Kp/128 elements), evaluates the candidates exactly
+//      and writes delta', the backpointer and, at a vector's last step, the final delta.  Several
+//      pairs per thread are in flight at once, so the two dependent memory round trips of a
+//      resolution are paid once per batch, not once per pair.
+struct PairRec {
+    float top;
+    int chain;  // lane | component << 8, or -1: ambiguous (several chains inside the window)
+};
+
 template <int QB, int RI, int NWARP>
 __global__ void __launch_bounds__(NWARP * 32) k_flash_group_pass(const GroupArgs a)
 {
-    extern __shared__ float4 sgroup4[];  // [2][QB][Kp/4]
+    extern __shared__ float4 sgroup4[];  // delta [2][QB][Kp] floats, then PairRec [QB][Kp], then VecDesc[QB]
     constexpr int NT = NWARP * 32;
     const int Kp4 = a.Kp >> 2;
     float *sbuf = reinterpret_cast<float *>(sgroup4);
+    PairRec *srec = reinterpret_cast<PairRec *>(sbuf + (size_t)2 * QB * a.Kp);
+    VecDesc *svd = reinterpret_cast<VecDesc *>(srec + (size_t)QB * a.Kp);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ngroups = (a.nvec + QB - 1) / QB;
+    const int chain_len = a.Kp >> 7;
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
         const int v0 = g * QB;
-        VecDesc vd[QB];
+        __syncthreads();  // previous group done with the buffers
+        if (tid < QB) {
+            VecDesc d = a.vecs[min(v0 + tid, a.nvec - 1)];
+            if (v0 + tid >= a.nvec) d.R = d.L;  // padding vector: no steps
+            svd[tid] = d;
+        }
+        __syncthreads();
         int gsteps = 0;
 #pragma unroll
-        for (int q = 0; q < QB; ++q) {
-            vd[q] = a.vecs[min(v0 + q, a.nvec - 1)];
-            if (v0 + q >= a.nvec) vd[q].R = vd[q].L;  // padding vector: no steps
-            gsteps = max(gsteps, vd[q].R - vd[q].L);
-        }
-        __syncthreads();  // previous group done with the buffers
+        for (int q = 0; q < QB; ++q) gsteps = max(gsteps, svd[q].R - svd[q].L);
         // start vectors, F:142 / F:220
 #pragma unroll
         for (int q = 0; q < QB; ++q) {
-            const int32_t *ob = a.ob + (size_t)vd[q].seq * a.T;
-            const int prev = vd[q].L == 0 ? -1 : a.ans[(size_t)vd[q].seq * a.T + vd[q].L - 1];
-            const int o = ob[vd[q].L];
+            const VecDesc d = svd[q];
+            const int prev = d.L == 0 ? -1 : a.ans[(size_t)d.seq * a.T + d.L - 1];
+            const int o = a.ob[(size_t)d.seq * a.T + d.L];
             for (int i = tid; i < a.Kp; i += NT) {
                 float v = 0.f;  // padding lanes stay finite (hiT pads with -inf)
                 if (i < a.K) {
@@ -246,25 +263,23 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_group_pass(const GroupArgs
             float *sout = sbuf + (size_t)(cur ^ 1) * QB * a.Kp;
             const float4 *sin4 = reinterpret_cast<const float4 *>(sin);
             const float *tmp_row[QB];
-            bool live[QB];
 #pragma unroll
             for (int q = 0; q < QB; ++q) {
-                live[q] = s <= vd[q].R - vd[q].L;
-                const int j = min(vd[q].L + s, vd[q].R);
-                tmp_row[q] = a.LBf + (size_t)a.ob[(size_t)vd[q].seq * a.T + j] * a.Kp;  // F:167
+                const VecDesc d = svd[q];
+                tmp_row[q] = a.LBf + (size_t)a.ob[(size_t)d.seq * a.T + min(d.L + s, d.R)] * a.Kp;  // F:167
             }
+            // ---- phase A ------------------------------------------------------------------
             for (int ibase = warp * RI; ibase < a.K; ibase += NWARP * RI) {
-                int col_i[RI];
                 const float4 *col4[RI];
                 float tmp[RI][QB];
                 float cm[RI][QB][4];
 #pragma unroll
                 for (int r = 0; r < RI; ++r) {
-                    col_i[r] = min(ibase + r, a.K - 1);
-                    col4[r] = reinterpret_cast<const float4 *>(a.hiT + (size_t)col_i[r] * a.Kp);
+                    const int ci = min(ibase + r, a.K - 1);
+                    col4[r] = reinterpret_cast<const float4 *>(a.hiT + (size_t)ci * a.Kp);
 #pragma unroll
                     for (int q = 0; q < QB; ++q) {
-                        tmp[r][q] = __ldg(tmp_row[q] + col_i[r]);
+                        tmp[r][q] = __ldg(tmp_row[q] + ci);
                         cm[r][q][0] = cm[r][q][1] = cm[r][q][2] = cm[r][q][3] = -INFINITY;
                     }
                 }
@@ -272,29 +287,106 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_group_pass(const GroupArgs
 #pragma unroll
                 for (int r = 0; r < RI; ++r) {
                     if (ibase + r >= a.K) continue;  // warp-uniform: the clamped duplicate column
-                    const int i = ibase + r;
-                    const float *pcol[QB];
-                    const float *pdelta[QB];
-                    int picol[QB];
-                    Best res[QB];
 #pragma unroll
                     for (int q = 0; q < QB; ++q) {
-                        picol[q] = i;
-                        pcol[q] = a.hiT + (size_t)i * a.Kp;
-                        pdelta[q] = sin + (size_t)q * a.Kp;
-                    }
-                    resolve_tile<QB>(cm[r], tmp[r], pcol, pdelta, picol, a.LAd, a.K, a.Kp, lane, res);
-                    if (lane == 0) {
+                        const float lm = fmaxf(fmaxf(cm[r][q][0], cm[r][q][1]), fmaxf(cm[r][q][2], cm[r][q][3]));
+                        const float top = warp_max(lm);
+                        const int thr = ford(top) - WINDOW_STEPS;
+                        const unsigned hit = __ballot_sync(FULL_MASK, ford(lm) >= thr);
+                        // the lanes inside the window say which of their components are
+                        int comps = 0;
 #pragma unroll
-                        for (int q = 0; q < QB; ++q) {
-                            if (!live[q]) continue;
-                            sout[(size_t)q * a.Kp + i] = res[q].x;
-                            const int j = vd[q].L + s;
-                            if (j >= vd[q].mid + 1)  // F:242
-                                psi_store(a.psi, a.psi16, (size_t)(vd[q].psi_row + (j - vd[q].mid - 1)) * a.K + i, res[q].k);
-                            if (j == vd[q].R) a.dfinal[(size_t)(v0 + q) * a.Kp + i] = res[q].x;
+                        for (int c = 0; c < 4; ++c) comps |= (ford(cm[r][q][c]) >= thr) << c;
+                        const int w = __ffs(hit) - 1;
+                        const int wc = __shfl_sync(FULL_MASK, comps, w < 0 ? 0 : w);
+                        const bool single = __popc(hit) == 1 && __popc(wc) == 1;
+                        if (lane == 0) {
+                            PairRec rec;
+                            rec.top = top;
+                            rec.chain = single ? (w | (__ffs(wc) - 1) << 8) : -1;
+                            srec[(size_t)q * a.Kp + ibase + r] = rec;
                         }
                     }
+                }
+            }
+            __syncthreads();
+            // ---- phase B ------------------------------------------------------------------
+            constexpr int UP = 4;  // pairs in flight per thread
+            const int npairs = QB * a.K;
+            for (int p0 = tid; p0 < npairs; p0 += NT * UP) {
+                int pi[UP], pq[UP], pw[UP], pc[UP], thr[UP];
+                float ptmp[UP];
+                bool ok[UP], simple[UP];
+                Best best[UP];
+#pragma unroll
+                for (int e = 0; e < UP; ++e) {
+                    const int p = p0 + e * NT;
+                    ok[e] = p < npairs;
+                    pq[e] = ok[e] ? p / a.K : 0;
+                    pi[e] = ok[e] ? p - pq[e] * a.K : 0;
+                    const PairRec rec = srec[(size_t)pq[e] * a.Kp + pi[e]];
+                    thr[e] = ford(rec.top) - WINDOW_STEPS;
+                    simple[e] = ok[e] && rec.chain >= 0 && rec.top > -FLT_MAX;
+                    pw[e] = rec.chain & 0xff, pc[e] = (rec.chain >> 8) & 3;
+                    best[e] = Best{-FLT_MAX, 0x7fffffff};  // a dead column (top <= -FLT_MAX) keeps this
+                }
+#pragma unroll
+                for (int e = 0; e < UP; ++e) {  // tmp of the pair's own vector (tmp_row[] is register-indexed)
+                    float t = 0.f;
+#pragma unroll
+                    for (int q = 0; q < QB; ++q)
+                        if (pq[e] == q) t = __ldg(tmp_row[q] + pi[e]);
+                    ptmp[e] = t;
+                }
+                // the one chain inside the window, element by element; UP pairs interleaved
+                for (int u = 0; u < chain_len; ++u) {
+                    float hv[UP], pre[UP];
+                    int kk[UP];
+                    bool in[UP];
+#pragma unroll
+                    for (int e = 0; e < UP; ++e) {
+                        kk[e] = 4 * (pw[e] + 32 * u) + pc[e];
+                        in[e] = simple[e] && kk[e] < a.K;
+                        hv[e] = in[e] ? __ldg(a.hiT + (size_t)pi[e] * a.Kp + kk[e]) : 0.f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < UP; ++e) {
+                        pre[e] = in[e] ? __fadd_rn(ptmp[e], sin[(size_t)pq[e] * a.Kp + kk[e]]) : 0.f;
+                        in[e] = in[e] && ford(__fadd_rn(pre[e], hv[e])) >= thr[e];
+                    }
+                    double la[UP];
+#pragma unroll
+                    for (int e = 0; e < UP; ++e) la[e] = in[e] ? __ldg(a.LAd + (size_t)kk[e] * a.K + pi[e]) : 0.0;
+#pragma unroll
+                    for (int e = 0; e < UP; ++e)
+                        if (in[e]) {
+                            const float x = exact_cand(pre[e], la[e]);
+                            if (x > -FLT_MAX) best_take(best[e], x, kk[e]);
+                        }
+                }
+#pragma unroll
+                for (int e = 0; e < UP; ++e) {
+                    if (!ok[e]) continue;
+                    const PairRec rec = srec[(size_t)pq[e] * a.Kp + pi[e]];
+                    if (rec.chain < 0 && rec.top > -FLT_MAX) {
+                        // ambiguous: every source state whose estimate is inside the window
+                        for (int k = 0; k < a.K; ++k) {
+                            const float pre = __fadd_rn(ptmp[e], sin[(size_t)pq[e] * a.Kp + k]);
+                            if (ford(__fadd_rn(pre, __ldg(a.hiT + (size_t)pi[e] * a.Kp + k))) >= thr[e]) {
+                                const float x = exact_cand(pre, __ldg(a.LAd + (size_t)k * a.K + pi[e]));
+                                if (x > -FLT_MAX) best_take(best[e], x, k);
+                            }
+                        }
+                    }
+                    Best b = best[e];
+                    if (!(b.x > -FLT_MAX)) b.x = -FLT_MAX, b.k = -1;
+                    const VecDesc d = svd[pq[e]];
+                    if (s > d.R - d.L) continue;  // this vector has finished
+                    const int i = pi[e], j = d.L + s;
+                    sout[(size_t)pq[e] * a.Kp + i] = b.x;
+                    if (j >= d.mid + 1)  // F:242
+                        psi_store(a.psi, a.psi16, (size_t)(d.psi_row + (j - d.mid - 1)) * a.K + i, b.k);
+                    if (j == d.R) a.dfinal[(size_t)(v0 + pq[e]) * a.Kp + i] = b.x;
                 }
             }
             __syncthreads();
@@ -445,8 +537,8 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
     const float *final_delta = d0;
     const bool persistent = p->engine == FLASHV_ENGINE_PERSISTENT && pass.nvec == 1;
     // many vectors over a table small enough that two delta sets of 8 vectors fit in shared memory
-    const bool grouped = p->engine != FLASHV_ENGINE_STEP && pass.nvec >= 2 * ctx->sm_count &&
-                         (size_t)2 * 8 * Kp * sizeof(float) <= 160 * 1024;
+    const size_t group_smem = (size_t)4 * 8 * Kp * sizeof(float) + 8 * sizeof(VecDesc);  // 2 delta sets + 8-byte pair records
+    const bool grouped = p->engine != FLASHV_ENGINE_STEP && pass.nvec >= 2 * ctx->sm_count && group_smem <= 200 * 1024;
     if (!grouped) {  // the group kernel builds its start vectors itself
         dim3 ig((K + 255) / 256, pass.nvec < 65535 ? pass.nvec : 65535);
         k_flash_init<<<ig, 256, 0, st>>>(vecs, pass.nvec, p->d_ob, p->d_ans, T, m->LAd, m->LBd, m->LPi, K, Kp, d0);
@@ -458,7 +550,7 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
         g.hiT = m->hiT, g.LAd = m->LAd, g.LBd = m->LBd, g.LPi = m->LPi, g.LBf = m->LBf, g.K = K, g.Kp = Kp;
         g.vecs = vecs, g.nvec = pass.nvec, g.ob = p->d_ob, g.ans = p->d_ans, g.T = T;
         g.dfinal = d1, g.psi = p->d_psi, g.psi16 = p->psi16;
-        const size_t smem = (size_t)2 * 8 * Kp * sizeof(float);
+        const size_t smem = group_smem;
         FV_CUDA(cudaFuncSetAttribute(k_flash_group_pass<8, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         int grid = ctx->sm_count;  // 512 threads x 128 registers: one CTA per SM, looping over groups
         const int ngroups = (pass.nvec + 7) / 8;
