@@ -60,6 +60,65 @@ __device__ void heap_replay_warp(const float *score, int K, int B, float *hv, in
         }
     }
     float mn = hv[0];
+    if (B >= 2 && B <= 128) {
+        // Streaming part for beams of up to 128 entries.  Which child a sift follows depends only on
+        // the heap, not on the new value, so the warp keeps one bit per internal node — "the right
+        // child is strictly smaller" (S:146) — in a 64-bit register.  The whole root-to-leaf
+        // min-child path then costs a few ALU operations; lane l fetches the entry at depth l, one
+        // ballot finds where the new value stops (S:152: first depth with v <= entry), lanes shift
+        // the entries above it up by one depth and refresh the bits of the nodes whose children
+        // changed.  Three shared-memory round trips per replacement instead of two per depth.
+        const int nparent = B / 2;
+        unsigned long long bits = 0;
+        for (int base = 0; base < nparent; base += 32) {
+            const int n = base + lane + 1;
+            const bool r = n <= nparent && 2 * n + 1 <= B && hv[2 * n - 1] > hv[2 * n];
+            bits |= (unsigned long long)__ballot_sync(FULL_MASK, r) << base;
+        }
+        for (int base = B; base < K; base += 32) {
+            const int i = base + lane;
+            const float s = i < K ? score[i] : -INFINITY;
+            unsigned enter = __ballot_sync(FULL_MASK, s > mn);
+            while (enter) {
+                const int l0 = __ffs(enter) - 1;
+                enter &= enter - 1;
+                const float v = __shfl_sync(FULL_MASK, s, l0);
+                if (!(v > mn)) continue;  // S:193, against the minimum as it is now
+                // node of the min-child path at this lane's depth (depth 0 = root)
+                int node = 1, mine = 0, depth = 0;
+                for (int d = 0; d < 8; ++d) {
+                    if (d == lane) mine = node;
+                    if (2 * node > B) break;
+                    node = 2 * node + (int)((bits >> (node - 1)) & 1ull);
+                    depth = d + 1;
+                }
+                if (lane == depth) mine = node;  // the last node reached (a leaf)
+                const bool on_path = lane >= 1 && lane <= depth;
+                const float cv = on_path ? hv[mine - 1] : 0.f;
+                const int cs = on_path ? hs[mine - 1] : 0;
+                const unsigned stopm = __ballot_sync(FULL_MASK, on_path && v <= cv);
+                const int stop = stopm ? __ffs(stopm) - 1 : depth + 1;  // v ends at depth stop-1
+                const int parent = __shfl_up_sync(FULL_MASK, mine, 1);
+                if (on_path && lane < stop) hv[parent - 1] = cv, hs[parent - 1] = cs;
+                const int place = __shfl_sync(FULL_MASK, mine, stop - 1);
+                if (lane == 0) hv[place - 1] = v, hs[place - 1] = base + l0;
+                __syncwarp();
+                // nodes at depths 0 .. stop-2 had a child replaced: refresh their bits
+                const bool upd = lane + 1 < stop && 2 * mine + 1 <= B;
+                const bool nb = upd && hv[2 * mine - 1] > hv[2 * mine];
+                const unsigned updm = __ballot_sync(FULL_MASK, upd), setm = __ballot_sync(FULL_MASK, nb);
+                for (unsigned m = updm; m; m &= m - 1) {
+                    const int l = __ffs(m) - 1;
+                    const int n = __shfl_sync(FULL_MASK, mine, l);
+                    const unsigned long long bit = 1ull << (n - 1);
+                    bits = (setm >> l & 1u) ? (bits | bit) : (bits & ~bit);
+                }
+                mn = hv[0];
+            }
+        }
+        __syncwarp();
+        return;
+    }
     for (int base = B; base < K; base += 32) {
         const int i = base + lane;
         const float s = i < K ? score[i] : -INFINITY;
