@@ -12,6 +12,9 @@
 // state psi_j[i] goes to the backpointer store and the payload is recovered by walking it back
 // from the end state, which is what the payload recursion of S:359-368 / S:448 computes forward.
 //   S: = /root/reference/src/FLASH_BS_Viterbi_multithread.c
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "flashv_internal.h"
 #include "trellis_common.cuh"
 
@@ -62,18 +65,24 @@ __device__ void heap_replay_warp(const float *score, int K, int B, float *hv, in
     float mn = hv[0];
     if (B >= 2 && B <= 128) {
         // Streaming part for beams of up to 128 entries.  Which child a sift follows depends only on
-        // the heap, not on the new value, so the warp keeps one bit per internal node — "the right
-        // child is strictly smaller" (S:146) — in a 64-bit register.  The whole root-to-leaf
-        // min-child path then costs a few ALU operations; lane l fetches the entry at depth l, one
-        // ballot finds where the new value stops (S:152: first depth with v <= entry), lanes shift
-        // the entries above it up by one depth and refresh the bits of the nodes whose children
-        // changed.  Three shared-memory round trips per replacement instead of two per depth.
-        const int nparent = B / 2;
-        unsigned long long bits = 0;
-        for (int base = 0; base < nparent; base += 32) {
-            const int n = base + lane + 1;
-            const bool r = n <= nparent && 2 * n + 1 <= B && hv[2 * n - 1] > hv[2 * n];
-            bits |= (unsigned long long)__ballot_sync(FULL_MASK, r) << base;
+        // the heap, not on the new value, so every lane keeps, per depth d, a bit mask "the right
+        // child of the j-th node of depth d is strictly smaller" (S:146).  The root-to-leaf min-child
+        // path is then a handful of ALU operations that every lane computes redundantly, so no
+        // shuffle is needed to agree on it: lane d fetches the entry at depth d, one ballot finds
+        // where the new value stops (S:152: first depth with v <= entry), lanes shift the entries
+        // above it up by one depth, and a second ballot refreshes the bits of the nodes whose
+        // children changed.  Three shared-memory round trips per replacement, none per depth.
+        constexpr int MAXD = 7;  // depth of node 128
+        unsigned long long dm[MAXD];  // dm[d] bit j: node 2^d + j prefers its right child (depths 0..6)
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d) {
+            dm[d] = 0;
+            const int first = 1 << d, count = 1 << d;
+            for (int base = 0; base < count; base += 32) {
+                const int n = first + base + lane;
+                const bool r = base + lane < count && 2 * n + 1 <= B && hv[2 * n - 1] > hv[2 * n];
+                dm[d] |= (unsigned long long)__ballot_sync(FULL_MASK, r) << base;
+            }
         }
         for (int base = B; base < K; base += 32) {
             const int i = base + lane;
@@ -82,38 +91,40 @@ __device__ void heap_replay_warp(const float *score, int K, int B, float *hv, in
             while (enter) {
                 const int l0 = __ffs(enter) - 1;
                 enter &= enter - 1;
-                const float v = __shfl_sync(FULL_MASK, s, l0);
+                const float v = score[base + l0];
                 if (!(v > mn)) continue;  // S:193, against the minimum as it is now
-                // node of the min-child path at this lane's depth (depth 0 = root)
-                int node = 1, mine = 0, depth = 0;
-                for (int d = 0; d < 8; ++d) {
-                    if (d == lane) mine = node;
-                    if (2 * node > B) break;
-                    node = 2 * node + (int)((bits >> (node - 1)) & 1ull);
-                    depth = d + 1;
+                // min-child path: jd[d] = index within depth d of the path node, depth = last depth
+                int jd[MAXD + 1];
+                int depth = 0;
+                jd[0] = 0;
+#pragma unroll
+                for (int d = 0; d < MAXD; ++d) {
+                    const int node = (1 << d) + jd[d];
+                    const bool more = depth == d && 2 * node <= B;
+                    jd[d + 1] = 2 * jd[d] + (int)((dm[d] >> jd[d]) & 1ull);
+                    if (more) depth = d + 1;
                 }
-                if (lane == depth) mine = node;  // the last node reached (a leaf)
+                int mine = 1, parent = 1;  // path node at this lane's depth and the one above it
+#pragma unroll
+                for (int d = 1; d <= MAXD; ++d)
+                    if (lane == d) mine = (1 << d) + jd[d], parent = (1 << (d - 1)) + jd[d - 1];
                 const bool on_path = lane >= 1 && lane <= depth;
                 const float cv = on_path ? hv[mine - 1] : 0.f;
                 const int cs = on_path ? hs[mine - 1] : 0;
                 const unsigned stopm = __ballot_sync(FULL_MASK, on_path && v <= cv);
                 const int stop = stopm ? __ffs(stopm) - 1 : depth + 1;  // v ends at depth stop-1
-                const int parent = __shfl_up_sync(FULL_MASK, mine, 1);
                 if (on_path && lane < stop) hv[parent - 1] = cv, hs[parent - 1] = cs;
-                const int place = __shfl_sync(FULL_MASK, mine, stop - 1);
-                if (lane == 0) hv[place - 1] = v, hs[place - 1] = base + l0;
+                if (lane == stop - 1) hv[mine - 1] = v, hs[mine - 1] = base + l0;  // lane 0 has mine == 1
                 __syncwarp();
                 // nodes at depths 0 .. stop-2 had a child replaced: refresh their bits
                 const bool upd = lane + 1 < stop && 2 * mine + 1 <= B;
                 const bool nb = upd && hv[2 * mine - 1] > hv[2 * mine];
                 const unsigned updm = __ballot_sync(FULL_MASK, upd), setm = __ballot_sync(FULL_MASK, nb);
-                for (unsigned m = updm; m; m &= m - 1) {
-                    const int l = __ffs(m) - 1;
-                    const int n = __shfl_sync(FULL_MASK, mine, l);
-                    const unsigned long long bit = 1ull << (n - 1);
-                    bits = (setm >> l & 1u) ? (bits | bit) : (bits & ~bit);
-                }
-                mn = hv[0];
+#pragma unroll
+                for (int d = 0; d < MAXD; ++d)
+                    if (updm >> d & 1u) dm[d] = (dm[d] & ~(1ull << jd[d])) | ((unsigned long long)(setm >> d & 1u) << jd[d]);
+                // the new minimum: the value itself if it stayed at the root, else the old depth-1 entry
+                mn = stop == 1 ? v : __shfl_sync(FULL_MASK, cv, 1);
             }
         }
         __syncwarp();
@@ -149,6 +160,7 @@ struct BsArgs {
     void *psi;
     int psi16;
     const uint8_t *ismid;
+    long long *trace;  // optional: per CTA {score cycles, heap cycles} (FLASHV_BS_TRACE), else null
 };
 
 // dynamic shared memory: float sscore[Kp]; float hv[2][B]; int hs[2][B]
@@ -181,7 +193,9 @@ __global__ void __launch_bounds__(1024) k_bs_pass(const BsArgs a)
     if (warp == 0) heap_replay_warp(sscore, K, B, hv0, hs0, lane);
     __syncthreads();
 
+    long long t_score = 0, t_heap = 0;
     for (int j = vd.L + 1; j <= vd.R; ++j) {
+        const long long c0 = clock64();
         const float *hv = hv0 + cur * B;
         const int *hs = hs0 + cur * B;
         const int o = ob[j];
@@ -212,10 +226,13 @@ __global__ void __launch_bounds__(1024) k_bs_pass(const BsArgs a)
             if (keep) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + i, arg < 0 ? -1 : hs[arg]);
         }
         __syncthreads();
+        const long long c1 = clock64();
         if (warp == 0) heap_replay_warp(sscore, K, B, hv0 + (cur ^ 1) * B, hs0 + (cur ^ 1) * B, lane);
         __syncthreads();
+        t_score += c1 - c0, t_heap += clock64() - c1;
         cur ^= 1;
     }
+    if (a.trace && tid == 0) a.trace[2 * v] = t_score, a.trace[2 * v + 1] = t_heap;
 
     if (tid == 0) {
         const float *hv = hv0 + cur * B;
@@ -258,6 +275,13 @@ int bs_run_pass(flashv_plan *p, const Pass &pass)
     a.vecs = p->d_vecs + pass.vec_offset, a.nvec = pass.nvec;
     a.ob = p->d_ob, a.ans = p->d_ans, a.score = p->d_score;
     a.psi = p->d_psi, a.psi16 = p->psi16, a.ismid = p->d_ismid;
+    a.trace = nullptr;
+    static long long *d_trace = nullptr;
+    const bool tracing = getenv("FLASHV_BS_TRACE") != nullptr;
+    if (tracing) {  // developer aid: cycles spent scoring vs rebuilding the heap, per vector
+        if (!d_trace) FV_CUDA(cudaMalloc(&d_trace, sizeof(long long) * 2 * 65536));
+        a.trace = pass.nvec <= 65536 ? d_trace : nullptr;
+    }
     const size_t smem = bs_smem_bytes(m->Kp, p->B);
     if (smem > (size_t)ctx->smem_optin) {
         set_error("FLASH-BS: K=%d, B=%d needs %zu bytes of shared memory per CTA (limit %d)", m->K, p->B, smem,
@@ -268,6 +292,13 @@ int bs_run_pass(flashv_plan *p, const Pass &pass)
     k_bs_pass<<<pass.nvec, 1024, smem, ctx->stream>>>(a);
     FV_CUDA(cudaGetLastError());
     ++p->launches;
+    if (a.trace) {
+        long long h[2];
+        FV_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        FV_CUDA(cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "[flashv bs trace] nvec=%d steps=%d vector 0: score %lld cycles, heap %lld cycles\n", pass.nvec,
+                pass.max_steps, h[0], h[1]);
+    }
     return FLASHV_OK;
 }
 
