@@ -322,12 +322,14 @@ __global__ void __launch_bounds__(256) k_bs_score_once(const double *__restrict_
     arg_out[i] = arg;
 }
 
-__global__ void k_bs_replay_once(const float *__restrict__ score, int K, int B, float *hv_out, int32_t *hs_out)
+__global__ void k_bs_replay_once(const float *__restrict__ score, int K, int B, float *hv_out, int32_t *hs_out, int debug)
 {
     extern __shared__ float smem_f[];
     float *hv = smem_f;
     int *hs = reinterpret_cast<int *>(smem_f + B);
+    const long long c0 = clock64();
     heap_replay_warp(score, K, B, hv, hs, threadIdx.x);
+    if (debug && threadIdx.x == 0) printf("[flashv] heap replay K=%d B=%d: %lld cycles (scores in global memory)\n", K, B, clock64() - c0);
     for (int s = threadIdx.x; s < B; s += 32) hv_out[s] = hv[s], hs_out[s] = hs[s];
 }
 
@@ -344,7 +346,7 @@ int bs_single_replay(flashv_ctx *ctx, const float *score_dev, int K, int B, floa
 {
     const size_t smem = (size_t)B * 8;
     FV_CUDA(cudaFuncSetAttribute(k_bs_replay_once, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_bs_replay_once<<<1, 32, smem, ctx->stream>>>(score_dev, K, B, hv_dev, hs_dev);
+    k_bs_replay_once<<<1, 32, smem, ctx->stream>>>(score_dev, K, B, hv_dev, hs_dev, getenv("FLASHV_BS_TRACE") != nullptr);
     FV_CUDA(cudaGetLastError());
     return FLASHV_OK;
 }

@@ -38,7 +38,7 @@ constexpr int NCONS = NCW * 32;       // consumer threads
 constexpr int NTHREADS = NCONS + 32;  // + producer warp
 constexpr int MAX_STAGES = 64;
 constexpr int TRACE_STEPS = 64, TRACE_PTS = 6;
-constexpr int CTRL_BYTES = 2 * MAX_STAGES * 8;  // full[], empty[]
+constexpr int CTRL_BYTES = 2 * MAX_STAGES * 8 + 64;  // full[], empty[], the TMEM base address slot
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,6 +116,40 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// ---- tensor memory as a second operand store ---------------------------------------------------
+// The stream phase is bound by shared-memory bandwidth (ring writes + tile reads + delta reads).
+// Blackwell's 256 KB of tensor memory per SM is idle in this kernel, so delta is mirrored there
+// once per step (tcgen05.st) and the inner loop reads it with tcgen05.ld — a different pipe —
+// instead of LDS.  Layout: a warp can only touch the 32 TMEM lanes of its quadrant (warp % 4), so
+// each quadrant holds a full copy: TMEM lane 32q+l, columns 4u..4u+3 = delta[4*(l+32u) .. +3],
+// exactly the float4 that lane l of any warp needs in iteration u.
+constexpr int TMEM_COLS = 128;  // power of two >= Kp/32 for Kp <= 4096
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(TMEM_COLS) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float4 &v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v.x)),
+                 "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float4 tmem_ld4(uint32_t taddr)
+{
+    uint32_t x, y, z, w;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(taddr) : "memory");
+    return make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z), __uint_as_float(w));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 struct PersistArgs {
     const float *hiC;  // CTA-tiled (float)log A, tile_geom.h
     const double *LAd;
@@ -331,6 +365,8 @@ __device__ __forceinline__ void scan_commit(Pending &p, const Scan &sc, const fl
     }
 }
 
+// TM: delta operand of the inner loop comes from tensor memory (Kp <= 4096) instead of shared memory.
+template <bool TM>
 __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -339,6 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
     constexpr uint32_t STAGE_BYTES = TILE_RW * TILE_CH * 4u;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *empty = full + MAX_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + MAX_STAGES);  // TMEM base address from tcgen05.alloc
     float4 *sdelta4 = reinterpret_cast<float4 *>(smem_raw + CTRL_BYTES);
     unsigned char *ring = reinterpret_cast<unsigned char *>(sdelta4 + Kp4);
 
@@ -352,7 +389,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
         for (int s = 0; s < a.nstage; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], NCW);
         mbar_fence_init();
     }
+    if (TM && warp == 0) tmem_alloc(tmem_slot);
+    if (TM) tmem_fence_before();
     __syncthreads();
+    if (TM) tmem_fence_after();
+    // this warp's window into tensor memory: its quadrant's lanes, column 0 of the allocation
+    const uint32_t tbase = TM ? (*tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16)) : 0u;
 
     if (warp == NCW) {
         // ---------------- producer: the slab, once per step, linearly through the ring -----------
@@ -393,6 +435,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
         long long *tr = tracing ? a.trace + ((((size_t)(s - 1) * G + b) * 2 + (warp == 0 ? 0 : 1)) * TRACE_PTS) : nullptr;
         if (tracing) tr[0] = clock64();
         delta_wait_load(a, s, reinterpret_cast<float *>(sdelta4), tid);
+        if (TM) {
+            // the warps of a quadrant (w, w+4, w+8, ...) share the work of refreshing its copy
+            const int members = (NCW - (warp & 3) + 3) / 4, me = warp >> 2;
+            for (int u = me; u * 32 < Kp4; u += members) tmem_st4(tbase + 4u * (uint32_t)u, sdelta4[32 * u + lane]);
+            tmem_wait_st();
+            tmem_fence_before();
+            named_bar_sync(1, NCONS);
+            tmem_fence_after();
+        }
         if (tracing) tr[1] = clock64();
 
         for (int rho = 0; rho < nrounds; ++rho) {
@@ -412,9 +463,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                 mbar_wait(&full[st], parity);
                 if (have0) {
                     if (u < nk_full) {
+                        float4 dt[TILE_CH / 128];
+                        if (TM) {
+#pragma unroll
+                            for (int it = 0; it < TILE_CH / 128; ++it) dt[it] = tmem_ld4(tbase + 4u * (uint32_t)(u * (TILE_CH / 128) + it));
+                            tmem_wait_ld();
+                        }
 #pragma unroll
                         for (int it = 0; it < TILE_CH / 128; ++it) {
-                            const float4 d = d4[it * 32];
+                            const float4 d = TM ? dt[it] : d4[it * 32];
                             const float4 h0 = stage4[row0 + it * 32];
                             const float4 h1 = stage4[row1 + it * 32];
                             cm0[0] = fmaxf(cm0[0], __fadd_rn(__fadd_rn(tmp0, d.x), h0.x));
@@ -479,6 +536,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
         named_bar_sync(1, NCONS);  // sdelta is overwritten by the next step's load
         if (tracing) tr[5] = clock64();
     }
+    if (TM) {
+        tmem_fence_before();
+        named_bar_sync(1, NCONS);
+        if (warp == 0) tmem_dealloc(*tmem_slot);
+    }
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -509,7 +571,8 @@ static int launch_persist(flashv_model *m, PersistArgs &a)
     a.nstage = nstage;
     a.l2_hint = env_int("FLASHV_L2_HINT", 1);
     const size_t smem = persist_smem(Kp, nstage);
-    const void *fn = (const void *)k_flash_persist;
+    const bool use_tmem = Kp <= 32 * TMEM_COLS && env_int("FLASHV_TMEM", 1) != 0;
+    const void *fn = use_tmem ? (const void *)k_flash_persist<true> : (const void *)k_flash_persist<false>;
     FV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     FV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NTHREADS, smem));
