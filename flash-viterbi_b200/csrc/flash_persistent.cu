@@ -116,14 +116,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// ---- tensor memory as a second operand store ---------------------------------------------------
-// The stream phase is bound by shared-memory bandwidth (ring writes + tile reads + delta reads).
-// Blackwell's 256 KB of tensor memory per SM is idle in this kernel, so delta is mirrored there
-// once per step (tcgen05.st) and the inner loop reads it with tcgen05.ld — a different pipe —
-// instead of LDS.  Layout: a warp can only touch the 32 TMEM lanes of its quadrant (warp % 4), so
-// each quadrant holds a full copy: TMEM lane 32q+l, columns 4u..4u+3 = delta[4*(l+32u) .. +3],
-// exactly the float4 that lane l of any warp needs in iteration u.
-constexpr int TMEM_COLS = 128;  // power of two >= Kp/32 for Kp <= 4096
+// ---- tensor memory as resident table storage ---------------------------------------------------
+// A CTA re-reads the same ~428 KB of log A every step, and what bounds the stream phase is the
+// rate at which L2 can refill the ring (~60 GB/s per SM while all 148 SMs pull).  Blackwell's
+// 256 KB of tensor memory per SM is idle in this kernel, so the first TM_RES_CHUNKS chunks (2048
+// source states) of every owned column are parked there ONCE, at kernel start (tcgen05.st), and
+// every step reads them back with tcgen05.ld; only the rest of each column goes through the ring
+// — little enough that the ring refills it completely while the CTAs hand over.
+// Layout: a warp can only touch the 32 TMEM lanes of its quadrant (warp % 4) and owns two fixed
+// columns, so warp w keeps its own data in columns [128*(w/4), +128) of its quadrant: for
+// iteration u (128 source states) TMEM lane l, columns 8u..8u+3 / 8u+4..8u+7 hold the float4 that
+// lane l needs for its first / second column.
+constexpr int TMEM_COLS = 512;     // the whole tensor memory of the SM
+constexpr int TM_RES_CHUNKS = 8;   // TILE_CH-sized chunks of every owned column kept resident (2048 states)
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(TMEM_COLS) : "memory");
@@ -365,7 +370,7 @@ __device__ __forceinline__ void scan_commit(Pending &p, const Scan &sc, const fl
     }
 }
 
-// TM: delta operand of the inner loop comes from tensor memory (Kp <= 4096) instead of shared memory.
+// TM: the first TM_RES_CHUNKS chunks of every owned column live in tensor memory (single-round CTAs only).
 template <bool TM>
 __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs a)
 {
@@ -393,8 +398,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
     if (TM) tmem_fence_before();
     __syncthreads();
     if (TM) tmem_fence_after();
-    // this warp's window into tensor memory: its quadrant's lanes, column 0 of the allocation
-    const uint32_t tbase = TM ? (*tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16)) : 0u;
+    // this warp's window into tensor memory: its quadrant's lanes, its own 128 columns
+    const uint32_t tbase = TM ? (*tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + 128u * (uint32_t)(warp >> 2)) : 0u;
+    const int nk_res = TM ? min(TM_RES_CHUNKS, a.Kp / TILE_CH) : 0;  // resident chunks (full ones only)
 
     if (warp == NCW) {
         // ---------------- producer: the slab, once per step, linearly through the ring -----------
@@ -406,7 +412,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(slab);
                 for (int rho = 0; rho < nrounds; ++rho) {
                     const int ncr = min(TILE_RW, ncols - rho * TILE_RW);
-                    for (int u = 0; u < nk; ++u) {
+                    src += (size_t)nk_res * TILE_CH * ncr * sizeof(float);  // resident chunks are not streamed
+                    for (int u = nk_res; u < nk; ++u) {
                         if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
                         const uint32_t bytes = (uint32_t)(ncr * min(TILE_CH, a.Kp - u * TILE_CH)) * 4u;
                         mbar_expect_tx(&full[st], bytes);
@@ -422,6 +429,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
 
     // ---------------- consumers ---------------------------------------------------------------
     const float *sdelta = reinterpret_cast<const float *>(sdelta4);
+    if (TM) {
+        // park the resident chunks of this warp's two columns (round 0 is the only round in TM mode)
+        const int ncr = ncols, rr0 = warp * CPW, rr1 = rr0 + 1;
+        if (rr0 < ncr) {
+            const int ra = rr0, rb = rr1 < ncr ? rr1 : rr0;
+            for (int u = 0; u < nk_res * (TILE_CH / 128); ++u) {
+                const int k = 4 * (lane + 32 * u);
+                tmem_st4(tbase + 8u * (uint32_t)u, __ldg(reinterpret_cast<const float4 *>(slab + tile_round_off(a.Kp, ncr, ra, k))));
+                tmem_st4(tbase + 8u * (uint32_t)u + 4u, __ldg(reinterpret_cast<const float4 *>(slab + tile_round_off(a.Kp, ncr, rb, k))));
+            }
+        }
+        tmem_wait_st();
+        tmem_fence_before();
+        named_bar_sync(1, NCONS);
+        tmem_fence_after();
+    }
     int st = 0;           // every consumer warp visits every ring item, in the producer's order
     uint32_t parity = 0;  // parity of the ring wrap count = phase parity to wait for
     const int nk_full = a.Kp / TILE_CH;  // chunks of exactly TILE_CH states; at most one shorter chunk follows
@@ -435,15 +458,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
         long long *tr = tracing ? a.trace + ((((size_t)(s - 1) * G + b) * 2 + (warp == 0 ? 0 : 1)) * TRACE_PTS) : nullptr;
         if (tracing) tr[0] = clock64();
         delta_wait_load(a, s, reinterpret_cast<float *>(sdelta4), tid);
-        if (TM) {
-            // the warps of a quadrant (w, w+4, w+8, ...) share the work of refreshing its copy
-            const int members = (NCW - (warp & 3) + 3) / 4, me = warp >> 2;
-            for (int u = me; u * 32 < Kp4; u += members) tmem_st4(tbase + 4u * (uint32_t)u, sdelta4[32 * u + lane]);
-            tmem_wait_st();
-            tmem_fence_before();
-            named_bar_sync(1, NCONS);
-            tmem_fence_after();
-        }
         if (tracing) tr[1] = clock64();
 
         for (int rho = 0; rho < nrounds; ++rho) {
@@ -458,30 +472,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             const int row0 = (have0 ? rr0 : 0) * (TILE_CH >> 2) + lane;
             const int row1 = (have1 ? rr1 : (have0 ? rr0 : 0)) * (TILE_CH >> 2) + lane;
             const float4 *d4 = sdelta4 + lane;
-            for (int u = 0; u < nk; ++u) {
+#define FV_ACC2(D, H0, H1)                                                  \
+    cm0[0] = fmaxf(cm0[0], __fadd_rn(__fadd_rn(tmp0, (D).x), (H0).x));      \
+    cm0[1] = fmaxf(cm0[1], __fadd_rn(__fadd_rn(tmp0, (D).y), (H0).y));      \
+    cm0[2] = fmaxf(cm0[2], __fadd_rn(__fadd_rn(tmp0, (D).z), (H0).z));      \
+    cm0[3] = fmaxf(cm0[3], __fadd_rn(__fadd_rn(tmp0, (D).w), (H0).w));      \
+    cm1[0] = fmaxf(cm1[0], __fadd_rn(__fadd_rn(tmp1, (D).x), (H1).x));      \
+    cm1[1] = fmaxf(cm1[1], __fadd_rn(__fadd_rn(tmp1, (D).y), (H1).y));      \
+    cm1[2] = fmaxf(cm1[2], __fadd_rn(__fadd_rn(tmp1, (D).z), (H1).z));      \
+    cm1[3] = fmaxf(cm1[3], __fadd_rn(__fadd_rn(tmp1, (D).w), (H1).w));
+            if (TM && have0) {
+                // the resident chunks: table operands from tensor memory, two iterations in flight
+                for (int u = 0; u < nk_res * (TILE_CH / 128); u += 2) {
+                    const float4 ha0 = tmem_ld4(tbase + 8u * (uint32_t)u), hb0 = tmem_ld4(tbase + 8u * (uint32_t)u + 4u);
+                    const float4 ha1 = tmem_ld4(tbase + 8u * (uint32_t)u + 8u), hb1 = tmem_ld4(tbase + 8u * (uint32_t)u + 12u);
+                    const float4 da = d4[u * 32], db = d4[u * 32 + 32];
+                    tmem_wait_ld();
+                    FV_ACC2(da, ha0, hb0)
+                    FV_ACC2(db, ha1, hb1)
+                }
+            }
+            d4 += nk_res * (TILE_CH >> 2);
+            for (int u = nk_res; u < nk; ++u) {
                 const float4 *stage4 = reinterpret_cast<const float4 *>(ring + (size_t)st * STAGE_BYTES);
                 mbar_wait(&full[st], parity);
                 if (have0) {
                     if (u < nk_full) {
-                        float4 dt[TILE_CH / 128];
-                        if (TM) {
-#pragma unroll
-                            for (int it = 0; it < TILE_CH / 128; ++it) dt[it] = tmem_ld4(tbase + 4u * (uint32_t)(u * (TILE_CH / 128) + it));
-                            tmem_wait_ld();
-                        }
 #pragma unroll
                         for (int it = 0; it < TILE_CH / 128; ++it) {
-                            const float4 d = TM ? dt[it] : d4[it * 32];
+                            const float4 d = d4[it * 32];
                             const float4 h0 = stage4[row0 + it * 32];
                             const float4 h1 = stage4[row1 + it * 32];
-                            cm0[0] = fmaxf(cm0[0], __fadd_rn(__fadd_rn(tmp0, d.x), h0.x));
-                            cm0[1] = fmaxf(cm0[1], __fadd_rn(__fadd_rn(tmp0, d.y), h0.y));
-                            cm0[2] = fmaxf(cm0[2], __fadd_rn(__fadd_rn(tmp0, d.z), h0.z));
-                            cm0[3] = fmaxf(cm0[3], __fadd_rn(__fadd_rn(tmp0, d.w), h0.w));
-                            cm1[0] = fmaxf(cm1[0], __fadd_rn(__fadd_rn(tmp1, d.x), h1.x));
-                            cm1[1] = fmaxf(cm1[1], __fadd_rn(__fadd_rn(tmp1, d.y), h1.y));
-                            cm1[2] = fmaxf(cm1[2], __fadd_rn(__fadd_rn(tmp1, d.z), h1.z));
-                            cm1[3] = fmaxf(cm1[3], __fadd_rn(__fadd_rn(tmp1, d.w), h1.w));
+                            FV_ACC2(d, h0, h1)
                         }
                     } else {  // the short last chunk: rows are len4 float4 apart
                         const int len4 = (a.Kp - u * TILE_CH) >> 2;
@@ -491,14 +513,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                             const float4 d = d4[t - lane];
                             const float4 h0 = p0[t];
                             const float4 h1 = p1[t];
-                            cm0[0] = fmaxf(cm0[0], __fadd_rn(__fadd_rn(tmp0, d.x), h0.x));
-                            cm0[1] = fmaxf(cm0[1], __fadd_rn(__fadd_rn(tmp0, d.y), h0.y));
-                            cm0[2] = fmaxf(cm0[2], __fadd_rn(__fadd_rn(tmp0, d.z), h0.z));
-                            cm0[3] = fmaxf(cm0[3], __fadd_rn(__fadd_rn(tmp0, d.w), h0.w));
-                            cm1[0] = fmaxf(cm1[0], __fadd_rn(__fadd_rn(tmp1, d.x), h1.x));
-                            cm1[1] = fmaxf(cm1[1], __fadd_rn(__fadd_rn(tmp1, d.y), h1.y));
-                            cm1[2] = fmaxf(cm1[2], __fadd_rn(__fadd_rn(tmp1, d.z), h1.z));
-                            cm1[3] = fmaxf(cm1[3], __fadd_rn(__fadd_rn(tmp1, d.w), h1.w));
+                            FV_ACC2(d, h0, h1)
                         }
                     }
                 }
@@ -536,6 +551,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
         named_bar_sync(1, NCONS);  // sdelta is overwritten by the next step's load
         if (tracing) tr[5] = clock64();
     }
+#undef FV_ACC2
     if (TM) {
         tmem_fence_before();
         named_bar_sync(1, NCONS);
@@ -571,7 +587,8 @@ static int launch_persist(flashv_model *m, PersistArgs &a)
     a.nstage = nstage;
     a.l2_hint = env_int("FLASHV_L2_HINT", 1);
     const size_t smem = persist_smem(Kp, nstage);
-    const bool use_tmem = Kp <= 32 * TMEM_COLS && env_int("FLASHV_TMEM", 1) != 0;
+    // tensor-memory residency needs every CTA to own at most one round of columns
+    const bool use_tmem = (a.K + m->tile_G - 1) / m->tile_G <= TILE_RW && Kp >= TILE_CH && env_int("FLASHV_TMEM", 1) != 0;
     const void *fn = use_tmem ? (const void *)k_flash_persist<true> : (const void *)k_flash_persist<false>;
     FV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
