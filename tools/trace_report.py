@@ -13,7 +13,14 @@ names = ["poll+stage delta", "stream+compute", "scan+exact", "publish", "end bar
 sel = slice(4, steps)  # skip the first steps (cold ring)
 for w, wn in enumerate(["warp 0", "last warp"]):
     print(wn)
-    for p in range(pts - 1):
+    if pts >= 7:  # point 6 sits between the tensor-memory part and the ring part of the stream phase
+        a_ = t[sel, :, w, 6] - t[sel, :, w, 1]
+        b_ = t[sel, :, w, 2] - t[sel, :, w, 6]
+        ok = (t[sel, :, w, 6] > 0) & (t[sel, :, w, 2] > 0)
+        if ok.any():
+            print(f"   {'  resident part':20s} mean {us(a_[ok].mean()):7.2f} us")
+            print(f"   {'  ring part':20s} mean {us(b_[ok].mean()):7.2f} us")
+    for p in range(5):
         d = t[sel, :, w, p + 1] - t[sel, :, w, p]
         ok = (t[sel, :, w, p + 1] > 0) & (t[sel, :, w, p] > 0)
         d = d[ok]
