@@ -447,6 +447,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
     }
     int st = 0;           // every consumer warp visits every ring item, in the producer's order
     uint32_t parity = 0;  // parity of the ring wrap count = phase parity to wait for
+    const int nk_full = a.Kp / TILE_CH;  // chunks of exactly TILE_CH states; at most one shorter chunk follows
     for (int s = 1; s <= a.nsteps; ++s) {
         unsigned long long *xout = a.xch + (size_t)(s & 1) * a.Kp;
         const bool last_step = s == a.nsteps;
@@ -467,6 +468,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             const float tmp0 = __ldg(tmp_row + i0), tmp1 = __ldg(tmp_row + i1);
             float cm0[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             float cm1[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            // row offsets inside a full stage, in float4 units; a duplicate row stands in for a missing one
+            const int row0 = (have0 ? rr0 : 0) * (TILE_CH >> 2) + lane;
+            const int row1 = (have1 ? rr1 : (have0 ? rr0 : 0)) * (TILE_CH >> 2) + lane;
             const float4 *d4 = sdelta4 + lane;
 #define FV_ACC2(D, H0, H1)                                                  \
     cm0[0] = fmaxf(cm0[0], __fadd_rn(__fadd_rn(tmp0, (D).x), (H0).x));      \
@@ -477,64 +481,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
     cm1[1] = fmaxf(cm1[1], __fadd_rn(__fadd_rn(tmp1, (D).y), (H1).y));      \
     cm1[2] = fmaxf(cm1[2], __fadd_rn(__fadd_rn(tmp1, (D).z), (H1).z));      \
     cm1[3] = fmaxf(cm1[3], __fadd_rn(__fadd_rn(tmp1, (D).w), (H1).w));
-            // One "iteration" = 128 source states: a float4 of delta and one of each owned column per
-            // lane.  Iterations 0 .. n_res-1 read the table from tensor memory, the rest from ring
-            // stages (IPC per full stage).  The loop is software-pipelined by hand: the operands of
-            // iteration n+1 are requested before iteration n is computed, and a stage is released
-            // right after its last iteration has been computed (its loads have landed by then).
-            constexpr int IPC = TILE_CH / 128;
-            const int n_res = nk_res * IPC;
-            const int n_ring = (a.Kp - nk_res * TILE_CH) >> 7;
-            if (have0) {
-                float4 cd, ch0, ch1, nd, nh0, nh1;
-                if (TM && n_res > 0) {
-                    ch0 = tmem_ld4(tbase), ch1 = tmem_ld4(tbase + 4u), cd = d4[0];
-                    for (int n = 0; n < n_res; ++n) {
-                        tmem_wait_ld();
-                        if (n + 1 < n_res) {
-                            nh0 = tmem_ld4(tbase + 8u * (uint32_t)(n + 1)), nh1 = tmem_ld4(tbase + 8u * (uint32_t)(n + 1) + 4u);
-                            nd = d4[(n + 1) * 32];
+            if (TM && have0) {
+                // the resident chunks: table operands from tensor memory, two iterations in flight
+                for (int u = 0; u < nk_res * (TILE_CH / 128); u += 2) {
+                    const float4 ha0 = tmem_ld4(tbase + 8u * (uint32_t)u), hb0 = tmem_ld4(tbase + 8u * (uint32_t)u + 4u);
+                    const float4 ha1 = tmem_ld4(tbase + 8u * (uint32_t)u + 8u), hb1 = tmem_ld4(tbase + 8u * (uint32_t)u + 12u);
+                    const float4 da = d4[u * 32], db = d4[u * 32 + 32];
+                    tmem_wait_ld();
+                    FV_ACC2(da, ha0, hb0)
+                    FV_ACC2(db, ha1, hb1)
+                }
+            }
+            d4 += nk_res * (TILE_CH >> 2);
+            if (tracing) tr[6] = clock64();
+            for (int u = nk_res; u < nk; ++u) {
+                const float4 *stage4 = reinterpret_cast<const float4 *>(ring + (size_t)st * STAGE_BYTES);
+                mbar_wait(&full[st], parity);
+                if (have0) {
+                    if (u < nk_full) {
+#pragma unroll
+                        for (int it = 0; it < TILE_CH / 128; ++it) {
+                            const float4 d = d4[it * 32];
+                            const float4 h0 = stage4[row0 + it * 32];
+                            const float4 h1 = stage4[row1 + it * 32];
+                            FV_ACC2(d, h0, h1)
                         }
-                        FV_ACC2(cd, ch0, ch1)
-                        cd = nd, ch0 = nh0, ch1 = nh1;
+                    } else {  // the short last chunk: rows are len4 float4 apart
+                        const int len4 = (a.Kp - u * TILE_CH) >> 2;
+                        const float4 *p0 = stage4 + (size_t)rr0 * len4;
+                        const float4 *p1 = have1 ? stage4 + (size_t)rr1 * len4 : p0;
+                        for (int t = lane; t < len4; t += 32) {
+                            const float4 d = d4[t - lane];
+                            const float4 h0 = p0[t];
+                            const float4 h1 = p1[t];
+                            FV_ACC2(d, h0, h1)
+                        }
                     }
                 }
-                if (tracing) tr[6] = clock64();
-                const float4 *dr = d4 + n_res * 32;  // delta of the first ring iteration
-                // ring cursor of the chunk being FETCHED (runs ahead of the one being computed)
-                int fst = st;
-                uint32_t fpar = parity;
-                auto fetch = [&](int m, float4 &d, float4 &h0, float4 &h1) {
-                    const int it = m % IPC, u = nk_res + m / IPC;
-                    if (it == 0) mbar_wait(&full[fst], fpar);
-                    const float4 *stage4 = reinterpret_cast<const float4 *>(ring + (size_t)fst * STAGE_BYTES);
-                    const int rs = min(TILE_CH, a.Kp - u * TILE_CH) >> 2;  // row stride of this chunk, float4
-                    d = dr[m * 32];
-                    h0 = stage4[rr0 * rs + it * 32 + lane];
-                    h1 = stage4[(have1 ? rr1 : rr0) * rs + it * 32 + lane];
-                    if (it == IPC - 1 || m == n_ring - 1)
-                        if (++fst == a.nstage) fst = 0, fpar ^= 1;
-                };
-                if (n_ring > 0) fetch(0, cd, ch0, ch1);
-                for (int m = 0; m < n_ring; ++m) {
-                    if (m + 1 < n_ring) fetch(m + 1, nd, nh0, nh1);
-                    FV_ACC2(cd, ch0, ch1)
-                    if (m % IPC == IPC - 1 || m == n_ring - 1) {  // last iteration of its chunk: release the stage
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty[st]);
-                        if (++st == a.nstage) st = 0, parity ^= 1;
-                    }
-                    cd = nd, ch0 = nh0, ch1 = nh1;
-                }
-            } else {
-                // a warp without a column in this round still takes part in the ring protocol
-                if (tracing) tr[6] = clock64();
-                for (int u = nk_res; u < nk; ++u) {
-                    mbar_wait(&full[st], parity);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[st]);
-                    if (++st == a.nstage) st = 0, parity ^= 1;
-                }
+                d4 += TILE_CH >> 2;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st]);
+                if (++st == a.nstage) st = 0, parity ^= 1;
             }
             if (tracing) tr[2] = clock64();
             if (!have0) continue;  // warp-uniform
