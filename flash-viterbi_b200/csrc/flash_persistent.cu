@@ -481,47 +481,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
     cm1[1] = fmaxf(cm1[1], __fadd_rn(__fadd_rn(tmp1, (D).y), (H1).y));      \
     cm1[2] = fmaxf(cm1[2], __fadd_rn(__fadd_rn(tmp1, (D).z), (H1).z));      \
     cm1[3] = fmaxf(cm1[3], __fadd_rn(__fadd_rn(tmp1, (D).w), (H1).w));
-            if (TM && have0) {
-                // the resident chunks: table operands from tensor memory, two iterations in flight
-                for (int u = 0; u < nk_res * (TILE_CH / 128); u += 2) {
-                    const float4 ha0 = tmem_ld4(tbase + 8u * (uint32_t)u), hb0 = tmem_ld4(tbase + 8u * (uint32_t)u + 4u);
-                    const float4 ha1 = tmem_ld4(tbase + 8u * (uint32_t)u + 8u), hb1 = tmem_ld4(tbase + 8u * (uint32_t)u + 12u);
-                    const float4 da = d4[u * 32], db = d4[u * 32 + 32];
-                    tmem_wait_ld();
-                    FV_ACC2(da, ha0, hb0)
-                    FV_ACC2(db, ha1, hb1)
-                }
-            }
-            d4 += nk_res * (TILE_CH >> 2);
-            if (tracing) tr[6] = clock64();
-            for (int u = nk_res; u < nk; ++u) {
-                const float4 *stage4 = reinterpret_cast<const float4 *>(ring + (size_t)st * STAGE_BYTES);
-                mbar_wait(&full[st], parity);
-                if (have0) {
-                    if (u < nk_full) {
+            // Tensor memory and shared memory are read through different pipes (TMEM ~64 B/clk, smem
+            // 128 B/clk per SM) and either one alone bounds its part, so odd warps walk the ring stages
+            // first and the resident chunks second: both pipes are busy for the whole phase.  The ring
+            // holds (almost) a whole step of streamed chunks, so the order does not stall the producer.
+            const bool ring_first = TM && (warp & 1);
+            const float4 *dring = d4 + nk_res * (TILE_CH >> 2);
+            for (int ph = 0; ph < 2; ++ph) {
+                const bool tm_now = TM && ((ph == 0) != ring_first);
+                if (tm_now) {
+                    if (have0) {
+                    // the resident chunks: table operands from tensor memory, four iterations per trip so
+                    // that one tcgen05.wait covers eight loads; the common full-residency case is unrolled
+                    // completely so every tcgen05.ld address is the base plus an immediate
+                    if (nk_res == TM_RES_CHUNKS) {
 #pragma unroll
-                        for (int it = 0; it < TILE_CH / 128; ++it) {
-                            const float4 d = d4[it * 32];
-                            const float4 h0 = stage4[row0 + it * 32];
-                            const float4 h1 = stage4[row1 + it * 32];
-                            FV_ACC2(d, h0, h1)
+                        for (int u = 0; u < TM_RES_CHUNKS * (TILE_CH / 128); u += 4) {
+                            float4 ha[4], hb[4], dd[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                ha[e] = tmem_ld4(tbase + 8u * (uint32_t)(u + e));
+                                hb[e] = tmem_ld4(tbase + 8u * (uint32_t)(u + e) + 4u);
+                                dd[e] = d4[(u + e) * 32];
+                            }
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { FV_ACC2(dd[e], ha[e], hb[e]) }
                         }
-                    } else {  // the short last chunk: rows are len4 float4 apart
-                        const int len4 = (a.Kp - u * TILE_CH) >> 2;
-                        const float4 *p0 = stage4 + (size_t)rr0 * len4;
-                        const float4 *p1 = have1 ? stage4 + (size_t)rr1 * len4 : p0;
-                        for (int t = lane; t < len4; t += 32) {
-                            const float4 d = d4[t - lane];
-                            const float4 h0 = p0[t];
-                            const float4 h1 = p1[t];
-                            FV_ACC2(d, h0, h1)
+                    } else {
+                        for (int u = 0; u < nk_res * (TILE_CH / 128); u += 2) {
+                            const float4 ha0 = tmem_ld4(tbase + 8u * (uint32_t)u), hb0 = tmem_ld4(tbase + 8u * (uint32_t)u + 4u);
+                            const float4 ha1 = tmem_ld4(tbase + 8u * (uint32_t)u + 8u), hb1 = tmem_ld4(tbase + 8u * (uint32_t)u + 12u);
+                            const float4 da = d4[u * 32], db = d4[u * 32 + 32];
+                            tmem_wait_ld();
+                            FV_ACC2(da, ha0, hb0)
+                            FV_ACC2(db, ha1, hb1)
                         }
                     }
                 }
-                d4 += TILE_CH >> 2;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[st]);
-                if (++st == a.nstage) st = 0, parity ^= 1;
+                } else if (TM || ph == 0) {
+                    for (int u = nk_res; u < nk; ++u) {
+                    const float4 *stage4 = reinterpret_cast<const float4 *>(ring + (size_t)st * STAGE_BYTES);
+                    mbar_wait(&full[st], parity);
+                    if (have0) {
+                        if (u < nk_full) {
+#pragma unroll
+                            for (int it = 0; it < TILE_CH / 128; ++it) {
+                                const float4 d = dring[it * 32];
+                                const float4 h0 = stage4[row0 + it * 32];
+                                const float4 h1 = stage4[row1 + it * 32];
+                                FV_ACC2(d, h0, h1)
+                            }
+                        } else {  // the short last chunk: rows are len4 float4 apart
+                            const int len4 = (a.Kp - u * TILE_CH) >> 2;
+                            const float4 *p0 = stage4 + (size_t)rr0 * len4;
+                            const float4 *p1 = have1 ? stage4 + (size_t)rr1 * len4 : p0;
+                            for (int t = lane; t < len4; t += 32) {
+                                const float4 d = dring[t - lane];
+                                const float4 h0 = p0[t];
+                                const float4 h1 = p1[t];
+                                FV_ACC2(d, h0, h1)
+                            }
+                        }
+                    }
+                    dring += TILE_CH >> 2;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[st]);
+                    if (++st == a.nstage) st = 0, parity ^= 1;
+                }
+                }
             }
             if (tracing) tr[2] = clock64();
             if (!have0) continue;  // warp-uniform
