@@ -31,7 +31,6 @@ import shutil
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 from pathlib import Path
 
@@ -62,40 +61,49 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed regions run (one streaming process,
+    a sample every 20 ms — the timed regions are only tens of milliseconds long)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            self._stop_evt.wait(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        rows = []
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            for ln in out.splitlines():
+                parts = [x.strip() for x in ln.split(",")]
+                if len(parts) >= 7:
+                    rows.append(parts)
+        num = lambda x: x.replace(".", "", 1).isdigit()
+        sm = sorted(float(r[0]) for r in rows if num(r[0]))
+        # "under load": samples drawing clearly more than idle power
+        pw = [float(r[2]) for r in rows if num(r[2])]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        mx = max((float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()), default=None)
+        mx = max((float(r[1]) for r in rows if num(r[1])), default=None)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+                "samples": len(rows), "power_w_max": max(pw) if pw else None}
 
 
 def synthetic(rank):
@@ -239,7 +247,6 @@ def run_ours(args):
             fp_ms.append(rep.first_pass_ms)
             launches += rep.kernel_launches
     barrier()
-    clocks = sampler.stop()
     dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
     dev_ms = max_over_ranks(dev_ms)
     value = world * K * K * T * args.steps / (dev_ms * 1e-3) / 1e9
@@ -254,6 +261,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
+    clocks = sampler.stop()
     e2e_value = world * K * K * T * args.steps / e2e_s / 1e9
 
     # the same decode at the reference-comparable segment counts, for the record (3 runs each)
