@@ -36,6 +36,8 @@ ABI_SYMBOLS = [
     "flashv_decode", "flashv_bs_decode", "flashv_decode_batch", "flashv_bs_decode_batch",
     "flashv_plan_create", "flashv_plan_destroy", "flashv_plan_upload", "flashv_plan_run",
     "flashv_plan_download", "flashv_plan_report",
+    "flashv_plan_shard_init", "flashv_plan_shard_buffers", "flashv_plan_shard_ipc_handles",
+    "flashv_plan_shard_set_peer", "flashv_plan_shard_open_peer",
     "flashv_trellis_init", "flashv_trellis_step", "flashv_bs_score_step", "flashv_bs_heap_replay",
     "flashv_task_list", "flashv_executed_steps", "flashv_memory_bytes", "flashv_bs_memory_bytes",
 ]
@@ -112,6 +114,11 @@ def lib():
     L.flashv_plan_run.argtypes = [vp]
     L.flashv_plan_download.argtypes = [vp, ip, fp]
     L.flashv_plan_report.argtypes = [vp, rp]
+    L.flashv_plan_shard_init.argtypes = [vp, C.c_int, C.c_int]
+    L.flashv_plan_shard_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.flashv_plan_shard_ipc_handles.argtypes = [vp, vp]
+    L.flashv_plan_shard_set_peer.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.flashv_plan_shard_open_peer.argtypes = [vp, C.c_int, vp]
     L.flashv_trellis_init.argtypes = [vp, C.c_int, C.c_int, fp]
     L.flashv_trellis_step.argtypes = [vp, fp, C.c_int, fp, ip, C.c_int]
     L.flashv_bs_score_step.argtypes = [vp, fp, ip, C.c_int, C.c_int, fp, ip]
@@ -330,6 +337,27 @@ class Plan:
     def download_ptr(self, path_ptr, score_ptr):
         _check(lib().flashv_plan_download(self._h, C.cast(C.c_void_p(path_ptr), C.POINTER(C.c_int32)),
                                           C.cast(C.c_void_p(score_ptr), C.POINTER(C.c_float))))
+
+    # ---- state sharding across GPUs (flashv_plan_shard_*) -------------------------------------
+    def shard_init(self, rank, world):
+        _check(lib().flashv_plan_shard_init(self._h, rank, world))
+
+    def shard_buffers(self):
+        d, s = C.c_void_p(), C.c_void_p()
+        _check(lib().flashv_plan_shard_buffers(self._h, C.byref(d), C.byref(s)))
+        return d.value, s.value
+
+    def shard_ipc_handles(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().flashv_plan_shard_ipc_handles(self._h, buf))
+        return buf.raw
+
+    def shard_set_peer(self, peer_rank, peer_device, delta_ptr, psi_ptr):
+        _check(lib().flashv_plan_shard_set_peer(self._h, peer_rank, peer_device, C.c_void_p(delta_ptr), C.c_void_p(psi_ptr)))
+
+    def shard_open_peer(self, peer_rank, handles: bytes):
+        buf = C.create_string_buffer(handles, 128)
+        _check(lib().flashv_plan_shard_open_peer(self._h, peer_rank, buf))
 
     def report(self):
         rep = Report()

@@ -265,9 +265,88 @@ extern "C" void flashv_plan_destroy(flashv_plan *p)
     if (!p) return;
     cudaSetDevice(p->model->ctx->device);
     cudaStreamSynchronize(p->model->ctx->stream);
+    for (int r = 0; r < 8; ++r)
+        if (p->peer_ipc[r]) cudaIpcCloseMemHandle(p->peer_delta[r]), cudaIpcCloseMemHandle(p->peer_psi[r]);
+    cudaFree(p->hiC_shard);
     cudaFree(p->d_ob), cudaFree(p->d_ans), cudaFree(p->d_score), cudaFree(p->d_delta), cudaFree(p->d_psi);
     cudaFree(p->d_vecs), cudaFree(p->d_ismid), cudaFree(p->d_endstate), cudaFree(p->d_sync), cudaFree(p->d_bs_score);
     delete p;
+}
+
+// ---- state sharding across GPUs ------------------------------------------------------
+extern "C" int flashv_plan_shard_init(flashv_plan *p, int rank, int world)
+{
+    if (!p || world < 1 || world > 8 || rank < 0 || rank >= world) {
+        set_error("flashv_plan_shard_init: rank %d of %d (at most 8 GPUs)", rank, world);
+        return FLASHV_ERR_ARG;
+    }
+    if (p->B != 0 || p->batch != 1 || p->engine != FLASHV_ENGINE_PERSISTENT) {
+        set_error("flashv_plan_shard_init: only single-sequence FLASH plans on the persistent engine shard their states");
+        return FLASHV_ERR_ARG;
+    }
+    if (p->hiC_shard) {
+        set_error("flashv_plan_shard_init: plan is already sharded");
+        return FLASHV_ERR_STATE;
+    }
+    FV_CUDA(cudaSetDevice(p->model->ctx->device));
+    p->shard_rank = rank, p->shard_world = world;
+    if (world == 1) return FLASHV_OK;
+    int rc = shard_build_table(p);
+    if (rc != FLASHV_OK) return rc;
+    p->peer_delta[rank] = p->d_delta, p->peer_psi[rank] = p->d_psi;
+    return FLASHV_OK;
+}
+
+extern "C" int flashv_plan_shard_buffers(flashv_plan *p, void **delta_base, void **psi_base)
+{
+    if (!p || !delta_base || !psi_base) return FLASHV_ERR_ARG;
+    *delta_base = p->d_delta, *psi_base = p->d_psi;
+    return FLASHV_OK;
+}
+
+extern "C" int flashv_plan_shard_ipc_handles(flashv_plan *p, void *out128)
+{
+    if (!p || !out128) return FLASHV_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "two handles fill 128 bytes");
+    FV_CUDA(cudaSetDevice(p->model->ctx->device));
+    cudaIpcMemHandle_t h[2];
+    FV_CUDA(cudaIpcGetMemHandle(&h[0], p->d_delta));
+    FV_CUDA(cudaIpcGetMemHandle(&h[1], p->d_psi));
+    memcpy(out128, h, sizeof(h));
+    return FLASHV_OK;
+}
+
+extern "C" int flashv_plan_shard_set_peer(flashv_plan *p, int peer_rank, int peer_device, void *delta_base, void *psi_base)
+{
+    if (!p || peer_rank < 0 || peer_rank >= p->shard_world || !delta_base || !psi_base) {
+        set_error("flashv_plan_shard_set_peer: bad argument");
+        return FLASHV_ERR_ARG;
+    }
+    flashv_ctx *ctx = p->model->ctx;
+    FV_CUDA(cudaSetDevice(ctx->device));
+    if (peer_device != ctx->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+        cudaGetLastError();
+    }
+    p->peer_delta[peer_rank] = (float *)delta_base, p->peer_psi[peer_rank] = psi_base;
+    return FLASHV_OK;
+}
+
+extern "C" int flashv_plan_shard_open_peer(flashv_plan *p, int peer_rank, const void *handles128)
+{
+    if (!p || peer_rank < 0 || peer_rank >= p->shard_world || !handles128 || peer_rank == p->shard_rank) {
+        set_error("flashv_plan_shard_open_peer: bad argument");
+        return FLASHV_ERR_ARG;
+    }
+    FV_CUDA(cudaSetDevice(p->model->ctx->device));
+    cudaIpcMemHandle_t h[2];
+    memcpy(h, handles128, sizeof(h));
+    void *d = nullptr, *s = nullptr;
+    FV_CUDA(cudaIpcOpenMemHandle(&d, h[0], cudaIpcMemLazyEnablePeerAccess));
+    FV_CUDA(cudaIpcOpenMemHandle(&s, h[1], cudaIpcMemLazyEnablePeerAccess));
+    p->peer_delta[peer_rank] = (float *)d, p->peer_psi[peer_rank] = s, p->peer_ipc[peer_rank] = true;
+    return FLASHV_OK;
 }
 
 extern "C" int flashv_plan_upload(flashv_plan *p, const int32_t *ob)

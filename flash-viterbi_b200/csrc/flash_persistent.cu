@@ -156,7 +156,8 @@ __device__ __forceinline__ float4 tmem_ld4(uint32_t taddr)
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct PersistArgs {
-    const float *hiC;  // CTA-tiled (float)log A, tile_geom.h
+    const float *hiC;  // CTA-tiled (float)log A of the columns [col_begin, col_begin+ncol), tile_geom.h
+    int col_begin, ncol;  // destination columns this GPU owns (all of them unless the pass is state-sharded)
     const double *LAd;
     const float *LBf;
     int K, Kp;
@@ -165,6 +166,12 @@ struct PersistArgs {
     const float *d_init;      // delta of the start vector (plain floats, written by k_flash_init)
     float *d_final;           // delta after the last step (plain floats, for k_flash_end)
     unsigned long long *xch;  // [2][Kp] exchange buffers of {value, step} words, zeroed before the launch
+    // state-sharded pass: every GPU publishes its slice of delta and of the backpointer
+    // rows into the buffers of ALL GPUs (peer stores over NVLink) and polls only its own copy
+    unsigned epoch;                    // run counter: step tags are (epoch << 16 | step), so stale words never match
+    int npeer;                         // GPUs taking part, this one included (1 = not sharded)
+    unsigned long long *xch_peer[8];   // their exchange buffers (entry `rank` is xch itself)
+    void *psi_peer[8];                 // their backpointer stores
     void *psi;
     int psi16;
     int nstage;
@@ -181,7 +188,8 @@ struct PersistArgs {
 // stores is needed.  Two buffers ping-pong: step s writes X[s&1] and reads X[(s-1)&1]; overwriting
 // X[s&1] at step s is safe because its previous content (step s-2) was read at the start of step
 // s-1, and a CTA can only be in step s once every CTA has published its step s-1 output, i.e. has
-// finished that read.  The buffers are zeroed before the launch (step numbers start at 1).
+// finished that read.  The step number is tagged with a per-run epoch, so words left over from an
+// earlier run (or not yet overwritten by a slower GPU) never match and nothing has to be cleared.
 __device__ __forceinline__ void ld_volatile_2x64(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
 {
     asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
@@ -191,6 +199,16 @@ __device__ __forceinline__ void publish_delta(unsigned long long *xch, int i, fl
 {
     const unsigned long long w = ((unsigned long long)(unsigned)step << 32) | (unsigned long long)__float_as_uint(v);
     asm volatile("st.global.u64 [%0], %1;" ::"l"(xch + i), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned step_tag(const PersistArgs &a, int step) { return (a.epoch << 16) | (unsigned)step; }
+// Sharded form: the word goes to every GPU.  The release orders this thread's earlier stores to
+// the same GPU (its backpointer entry) before the tagged word, which is what the final hand-shake
+// of the pass relies on; during the pass nothing depends on that order.
+__device__ __forceinline__ void publish_delta_peers(const PersistArgs &a, int parity, int i, float v, int step)
+{
+    const unsigned long long w = ((unsigned long long)step_tag(a, step) << 32) | (unsigned long long)__float_as_uint(v);
+    for (int r = 0; r < a.npeer; ++r)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.xch_peer[r] + (size_t)parity * a.Kp + i), "l"(w) : "memory");
 }
 
 // Stage delta_{s-1} in shared memory: from the plain start vector for s == 1, else from the
@@ -211,7 +229,7 @@ __device__ __forceinline__ void delta_wait_load(const PersistArgs &a, int s, flo
         // All of a thread's entries are requested before any is inspected, so a step pays one L2
         // round trip here when the data is already there, not one per entry.
         const unsigned long long *x = a.xch + (size_t)((s - 1) & 1) * a.Kp;
-        const unsigned want = (unsigned)(s - 1);
+        const unsigned want = step_tag(a, s - 1);
         constexpr int NB = 8;  // entries (pairs of delta values) in flight per thread
         for (int t0 = ctid; t0 < Kp2; t0 += NCONS * NB) {
             unsigned long long w0[NB], w1[NB];
@@ -386,7 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, b = blockIdx.x;
-    const int c0 = tile_c0(a.K, G, b), ncols = tile_c0(a.K, G, b + 1) - c0;
+    const int c0 = tile_c0(a.ncol, G, b), ncols = tile_c0(a.ncol, G, b + 1) - c0;  // local column indices
     const int nrounds = (ncols + TILE_RW - 1) / TILE_RW;
     const float *slab = a.hiC + (size_t)c0 * a.Kp;  // this CTA's columns: ncols*Kp floats, in stream order
 
@@ -464,7 +482,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             const int ncr = min(TILE_RW, ncols - rho * TILE_RW);
             const int rr0 = warp * CPW, rr1 = rr0 + 1;
             const bool have0 = rr0 < ncr, have1 = rr1 < ncr;
-            const int i0 = c0 + rho * TILE_RW + (have0 ? rr0 : 0), i1 = c0 + rho * TILE_RW + (have1 ? rr1 : 0);
+            const int i0 = a.col_begin + c0 + rho * TILE_RW + (have0 ? rr0 : 0);  // global state indices
+            const int i1 = a.col_begin + c0 + rho * TILE_RW + (have1 ? rr1 : 0);
             const float tmp0 = __ldg(tmp_row + i0), tmp1 = __ldg(tmp_row + i1);
             float cm0[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             float cm1[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -563,16 +582,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             if (tracing) tr[3] = clock64();
             const Best r0 = pending_finish(q0);
             if (lane == 0) {
-                publish_delta(xout, i0, r0.x, s);
-                if (last_step) a.d_final[i0] = r0.x;
-                if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i0, r0.k);
+                if (a.npeer > 1) {
+                    if (keep)
+                        for (int r = 0; r < a.npeer; ++r)
+                            psi_store(a.psi_peer[r], a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i0, r0.k);
+                    publish_delta_peers(a, s & 1, i0, r0.x, s);
+                } else {
+                    publish_delta(xout, i0, r0.x, (int)step_tag(a, s));
+                    if (last_step) a.d_final[i0] = r0.x;
+                    if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i0, r0.k);
+                }
             }
             if (have1) {
                 const Best r1 = pending_finish(q1);
                 if (lane == 0) {
-                    publish_delta(xout, i1, r1.x, s);
-                    if (last_step) a.d_final[i1] = r1.x;
-                    if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i1, r1.k);
+                    if (a.npeer > 1) {
+                        if (keep)
+                            for (int r = 0; r < a.npeer; ++r)
+                                psi_store(a.psi_peer[r], a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i1, r1.k);
+                        publish_delta_peers(a, s & 1, i1, r1.x, s);
+                    } else {
+                        publish_delta(xout, i1, r1.x, (int)step_tag(a, s));
+                        if (last_step) a.d_final[i1] = r1.x;
+                        if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i1, r1.k);
+                    }
                 }
             }
         }
@@ -581,6 +614,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
         if (tracing) tr[5] = clock64();
     }
 #undef FV_ACC2
+    if (a.npeer > 1) {
+        // Final hand-shake of a sharded pass: wait until every GPU's last delta slice has arrived
+        // here (their release stores order their backpointer entries before it), acquire, and
+        // leave the complete final vector where k_flash_end expects it.
+        delta_wait_load(a, a.nsteps + 1, reinterpret_cast<float *>(sdelta4), tid);
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        if (b == 0)
+            for (int i = tid; i < a.K; i += NCONS) a.d_final[i] = sdelta[i];
+    }
     if (TM) {
         tmem_fence_before();
         named_bar_sync(1, NCONS);
@@ -617,7 +659,8 @@ static int launch_persist(flashv_model *m, PersistArgs &a)
     a.l2_hint = env_int("FLASHV_L2_HINT", 1);
     const size_t smem = persist_smem(Kp, nstage);
     // tensor-memory residency needs every CTA to own at most one round of columns
-    const bool use_tmem = (a.K + m->tile_G - 1) / m->tile_G <= TILE_RW && Kp >= TILE_CH && env_int("FLASHV_TMEM", 1) != 0;
+    const int grid = ctx->sm_count < a.ncol ? ctx->sm_count : a.ncol;  // the grid the tiled table was laid out for
+    const bool use_tmem = (a.ncol + grid - 1) / grid <= TILE_RW && Kp >= TILE_CH && env_int("FLASHV_TMEM", 1) != 0;
     const void *fn = use_tmem ? (const void *)k_flash_persist<true> : (const void *)k_flash_persist<false>;
     FV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -626,11 +669,10 @@ static int launch_persist(flashv_model *m, PersistArgs &a)
         set_error("persistent engine: kernel does not fit one CTA per SM");
         return FLASHV_ERR_CUDA;
     }
-    FV_CUDA(cudaMemsetAsync(a.xch, 0, (size_t)2 * a.Kp * sizeof(unsigned long long), ctx->stream));
     // developer aid: FLASHV_TRACE_FILE=<path> dumps per-step phase timestamps of the last launch
     const char *trace_path = a.nsteps >= TRACE_STEPS ? getenv("FLASHV_TRACE_FILE") : nullptr;
     static long long *d_trace = nullptr;
-    const size_t trace_n = (size_t)TRACE_STEPS * m->tile_G * 2 * TRACE_PTS;
+    const size_t trace_n = (size_t)TRACE_STEPS * grid * 2 * TRACE_PTS;
     a.trace = nullptr;
     if (trace_path) {
         if (!d_trace) FV_CUDA(cudaMalloc(&d_trace, trace_n * sizeof(long long)));
@@ -640,13 +682,13 @@ static int launch_persist(flashv_model *m, PersistArgs &a)
     void *params[] = {(void *)&a};
     // cooperative launch: every CTA polls data the others produce, so all must be co-resident;
     // the grid is the one the tiled table was laid out for
-    FV_CUDA(cudaLaunchCooperativeKernel(fn, dim3(m->tile_G), dim3(NTHREADS), params, smem, ctx->stream));
+    FV_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NTHREADS), params, smem, ctx->stream));
     if (trace_path) {
         std::vector<long long> h(trace_n);
         FV_CUDA(cudaMemcpyAsync(h.data(), d_trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         FV_CUDA(cudaStreamSynchronize(ctx->stream));
         if (FILE *fp = fopen(trace_path, "wb")) {
-            const int hdr[4] = {TRACE_STEPS, m->tile_G, 2, TRACE_PTS};
+            const int hdr[4] = {TRACE_STEPS, grid, 2, TRACE_PTS};
             fwrite(hdr, sizeof(hdr), 1, fp);
             fwrite(h.data(), sizeof(long long), trace_n, fp);
             fclose(fp);
@@ -660,15 +702,58 @@ int persistent_pass(flashv_plan *p, const Pass &pass)
     flashv_model *m = p->model;
     const VecDesc &vd = pass.first_vec;  // the pass has exactly one vector (batch == 1)
     PersistArgs a;
-    a.hiC = m->hiC, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+    a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.ob = p->d_ob;
     a.L = vd.L, a.nsteps = vd.R - vd.L, a.mid = vd.mid, a.psi_row = vd.psi_row;
     a.d_init = p->d_delta, a.d_final = p->d_delta + (size_t)p->max_vec * m->Kp;
     a.xch = reinterpret_cast<unsigned long long *>(p->d_delta + (size_t)2 * p->max_vec * m->Kp);
     a.psi = p->d_psi, a.psi16 = p->psi16;
+    a.epoch = (++p->run_epoch) & 0xffffu;
+    if (a.epoch == 0) a.epoch = (++p->run_epoch) & 0xffffu;  // tag 0 is what a fresh buffer holds
+    if (p->shard_world > 1) {
+        // state-sharded: this GPU owns the columns [shard_c0, shard_c0 + shard_ncol) and publishes
+        // into every GPU's buffers (same offsets in every plan: identical plan parameters)
+        if (a.nsteps >= 65536) {
+            set_error("state-sharded pass: more than 65535 steps");
+            return FLASHV_ERR_ARG;
+        }
+        a.hiC = p->hiC_shard, a.col_begin = p->shard_c0, a.ncol = p->shard_ncol, a.npeer = p->shard_world;
+        for (int r = 0; r < p->shard_world; ++r) {
+            if (!p->peer_delta[r] || !p->peer_psi[r]) {
+                set_error("state-sharded pass: peer %d has not been connected", r);
+                return FLASHV_ERR_STATE;
+            }
+            a.xch_peer[r] = reinterpret_cast<unsigned long long *>(p->peer_delta[r] + (size_t)2 * p->max_vec * m->Kp);
+            a.psi_peer[r] = p->peer_psi[r];
+        }
+    } else {
+        a.hiC = m->hiC, a.col_begin = 0, a.ncol = m->K, a.npeer = 1;
+        a.xch_peer[0] = a.xch, a.psi_peer[0] = a.psi;
+    }
     int rc = launch_persist(m, a);
     if (rc == FLASHV_OK) p->launches += 1;
     return rc;
+}
+
+// ---- state sharding: this GPU's column slice of the tiled table ------------------------
+int shard_build_table(flashv_plan *p)
+{
+    flashv_model *m = p->model;
+    flashv_ctx *ctx = m->ctx;
+    const int K = m->K, Kp = m->Kp;
+    p->shard_c0 = (int)((long long)p->shard_rank * K / p->shard_world);
+    p->shard_ncol = (int)((long long)(p->shard_rank + 1) * K / p->shard_world) - p->shard_c0;
+    if (p->shard_ncol < 1) {
+        set_error("state sharding: rank %d of %d owns no column of K=%d", p->shard_rank, p->shard_world, K);
+        return FLASHV_ERR_ARG;
+    }
+    const int grid = ctx->sm_count < p->shard_ncol ? ctx->sm_count : p->shard_ncol;
+    FV_CUDA(cudaMalloc(&p->hiC_shard, (size_t)p->shard_ncol * Kp * sizeof(float)));
+    p->bytes += (size_t)p->shard_ncol * Kp * sizeof(float);
+    build_tiled_slice(m->LAd, p->hiC_shard, K, Kp, p->shard_c0, p->shard_ncol, grid, ctx->stream);
+    FV_CUDA(cudaGetLastError());
+    FV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FLASHV_OK;
 }
 
 int persistent_single_step(flashv_model *m, const float *d_in_dev, int o, float *d_out_dev, int32_t *psi_dev)
@@ -679,11 +764,15 @@ int persistent_single_step(flashv_model *m, const float *d_in_dev, int o, float 
     FV_CUDA(cudaMemcpyAsync(dob, hob, sizeof(hob), cudaMemcpyHostToDevice, ctx->stream));
     FV_CUDA(cudaStreamSynchronize(ctx->stream));
     PersistArgs a;
-    a.hiC = m->hiC, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+    a.hiC = m->hiC, a.col_begin = 0, a.ncol = m->K, a.npeer = 1;
+    a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.ob = dob, a.L = 0, a.nsteps = 1, a.mid = 0, a.psi_row = 0;
+    static unsigned hook_epoch = 0;
+    a.epoch = (++hook_epoch & 0xffffu) ? (hook_epoch & 0xffffu) : (++hook_epoch & 0xffffu);
     a.d_init = d_in_dev, a.d_final = d_out_dev;
     a.xch = reinterpret_cast<unsigned long long *>(m->scratch_x);
     a.psi = psi_dev, a.psi16 = 0;
+    a.xch_peer[0] = a.xch, a.psi_peer[0] = a.psi;
     return launch_persist(m, a);
 }
 

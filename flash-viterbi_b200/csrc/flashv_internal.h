@@ -117,6 +117,14 @@ struct flashv_plan {
     uint8_t *d_ismid = nullptr;   // [T] 1 where a first-pass segment boundary sits
     int32_t *d_endstate = nullptr;  // [max_vec]
     unsigned int *d_sync = nullptr; // grid-barrier words of the persistent engine
+    // state sharding of single-vector passes
+    int shard_rank = 0, shard_world = 1;
+    int shard_c0 = 0, shard_ncol = 0;   // destination columns this GPU owns
+    float *hiC_shard = nullptr;         // their slice of the tiled table
+    float *peer_delta[8] = {};          // every GPU's d_delta block (own entry included)
+    void *peer_psi[8] = {};             // every GPU's backpointer store
+    bool peer_ipc[8] = {};              // opened with cudaIpcOpenMemHandle (to be closed)
+    unsigned run_epoch = 0;             // tags the exchange words of one run
     // FLASH-BS
     float *d_bs_score = nullptr;  // [max_vec][Kp]
     size_t bytes = 0;
@@ -130,6 +138,8 @@ struct flashv_plan {
 namespace flashv {
 
 int tables_build(flashv_model *m, const float *A, const float *B, const float *Pi);
+void build_tiled_slice(const double *LAd, float *hiC, int K, int Kp, int col_begin, int ncol, int G, cudaStream_t st);
+int shard_build_table(flashv_plan *p);
 
 int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it);
 int bs_run_pass(flashv_plan *p, const Pass &pass);

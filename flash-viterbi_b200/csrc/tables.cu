@@ -48,13 +48,21 @@ __global__ void k_transpose_to_f32(const double *__restrict__ LAd, float *__rest
 
 // hiC: the same numbers CTA-tiled for the persistent engine (tile_geom.h).  One thread per (k, i),
 // reads coalesced along i from the hiT-independent double table, scattered 4-byte writes.
-__global__ void k_build_tiled(const double *__restrict__ LAd, float *__restrict__ hiC, int K, int Kp, int G)
+// The slice form serves the state-sharded pass: only the columns [col_begin, col_begin+ncol),
+// tiled for a grid of G CTAs over those ncol columns.
+__global__ void k_build_tiled(const double *__restrict__ LAd, float *__restrict__ hiC, int K, int Kp, int col_begin,
+                              int ncol, int G)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;  // column index inside the slice
     const int k = blockIdx.y;
-    if (i >= K) return;
-    const float v = k < K ? __double2float_rn(LAd[(size_t)k * K + i]) : -INFINITY;
-    hiC[tile_off(K, Kp, G, i, k)] = v;
+    if (il >= ncol) return;
+    const float v = k < K ? __double2float_rn(LAd[(size_t)k * K + col_begin + il]) : -INFINITY;
+    hiC[tile_off(ncol, Kp, G, il, k)] = v;
+}
+
+void build_tiled_slice(const double *LAd, float *hiC, int K, int Kp, int col_begin, int ncol, int G, cudaStream_t st)
+{
+    k_build_tiled<<<dim3((ncol + 255) / 256, Kp), 256, 0, st>>>(LAd, hiC, K, Kp, col_begin, ncol, G);
 }
 
 static bool in_unit(const float *p, size_t n)
@@ -137,7 +145,7 @@ int tables_build(flashv_model *m, const float *A, const float *B, const float *P
     k_transpose_to_f32<<<grid, block, 0, ctx->stream>>>(m->LAd, m->hiT, K, Kp);
     TB_CUDA(cudaGetLastError());
     m->tile_G = ctx->sm_count < K ? ctx->sm_count : K;
-    k_build_tiled<<<dim3((K + 255) / 256, Kp), 256, 0, ctx->stream>>>(m->LAd, m->hiC, K, Kp, m->tile_G);
+    build_tiled_slice(m->LAd, m->hiC, K, Kp, 0, K, m->tile_G, ctx->stream);
     TB_CUDA(cudaGetLastError());
     TB_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef TB_CUDA

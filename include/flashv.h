@@ -105,6 +105,21 @@ int flashv_plan_run(flashv_plan *plan);                                       /*
 int flashv_plan_download(flashv_plan *plan, int32_t *path_out, float *score_out); /* D2H + stream sync */
 int flashv_plan_report(flashv_plan *plan, flashv_report *report);            /* of the last run (syncs) */
 
+/* ---- state sharding of one huge K across the GPUs of a box -------------------- */
+/* Every rank holds the full model and an identical FLASH plan (batch 1, persistent engine).  After
+ * flashv_plan_shard_init(plan, rank, world) a rank computes only its slice of destination states
+ * in every single-vector pass (the N-way first pass of F:126-202); each step it stores its slice
+ * of delta and of the backpointer row into the buffers of ALL ranks with in-kernel peer stores over
+ * NVLink and polls only its own copy — the per-step all-gather, with no host or NCCL call.  The tree
+ * levels then run replicated.  Ranks exchange their buffers once: raw pointers inside one process
+ * (set_peer enables peer access), cudaIpc handles between processes (128 bytes per rank, e.g. through
+ * torch.distributed.all_gather).  All ranks must call flashv_plan_run together (barrier first). */
+int flashv_plan_shard_init(flashv_plan *plan, int rank, int world);
+int flashv_plan_shard_buffers(flashv_plan *plan, void **delta_base, void **psi_base);
+int flashv_plan_shard_ipc_handles(flashv_plan *plan, void *out128);
+int flashv_plan_shard_set_peer(flashv_plan *plan, int peer_rank, int peer_device, void *delta_base, void *psi_base);
+int flashv_plan_shard_open_peer(flashv_plan *plan, int peer_rank, const void *handles128);
+
 /* ---- pieces of the pass, exposed for per-step parity tests ---------------------------- */
 /* Start vector of nvviter / nvviterNdivide (F:142, F:220): prev_state < 0 selects the pi form. */
 int flashv_trellis_init(flashv_model *model, int prev_state, int ob0, float *delta_out);
