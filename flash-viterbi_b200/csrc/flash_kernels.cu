@@ -493,13 +493,9 @@ template <int QB, int RI, int NWARP>
 static cudaError_t launch_step(const StepArgs &a, int nact, int sm_count, cudaStream_t st)
 {
     const size_t smem = (size_t)QB * a.Kp * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e =
-            cudaFuncSetAttribute(k_flash_step<QB, RI, NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // per launch, not once per process: the attribute is per device and a process may drive several
+    cudaError_t e = cudaFuncSetAttribute(k_flash_step<QB, RI, NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
     const int ngroups = (nact + QB - 1) / QB;
     const int ntiles = (a.K + NWARP * RI - 1) / (NWARP * RI);
     // blocks that fit at once (shared memory bound), spread over the vector groups
