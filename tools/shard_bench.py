@@ -1,0 +1,79 @@
+#!/usr/bin/env python3
+"""State-sharded first pass: one process drives `world` GPUs, each owning a slice of the
+destination states; per step the slices are exchanged with in-kernel peer stores.  Prints the device
+time of the full-length pass on rank 0 for world = 1, 2, 4, ... (as many GPUs as are visible)."""
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "flash-viterbi_b200" / "host"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from __graft_entry__ import load_pkg  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--K", type=int, default=16384)
+    ap.add_argument("--T", type=int, default=64)
+    ap.add_argument("--N", type=int, default=16)
+    ap.add_argument("--p", type=float, default=0.02)
+    ap.add_argument("--iters", type=int, default=3)
+    a = ap.parse_args()
+    import gen_hmm
+
+    fv = load_pkg()
+    t0 = time.time()
+    A, B, Pi = gen_hmm.make_hmm(a.K, 50, a.p, 1)
+    f = gen_hmm.as_reference_floats
+    A, B, Pi = f(A), f(B), f(Pi)
+    ob = gen_hmm.observations(a.T, 50, 1000)
+    ngpu = torch.cuda.device_count()
+    print(f"K={a.K} T={a.T} N={a.N}: HMM generated in {time.time() - t0:.1f} s, {ngpu} GPU(s) visible", flush=True)
+    ctxs = [fv.Context(r) for r in range(ngpu)]
+    models = [fv.Model(c, A, B, Pi) for c in ctxs]
+    print(f"model prep {models[0].prep_ms:.0f} ms per GPU", flush=True)
+    base_path = None
+    out = {}
+    world = 1
+    while world <= ngpu:
+        plans = [fv.Plan(models[r], a.T, a.N, 1, 0, fv.ENGINE_PERSISTENT) for r in range(world)]
+        for r, p in enumerate(plans):
+            p.shard_init(r, world)
+        bufs = [p.shard_buffers() for p in plans]
+        for r, p in enumerate(plans):
+            for q in range(world):
+                if q != r:
+                    p.shard_set_peer(q, q, bufs[q][0], bufs[q][1])
+        best = None
+        for it in range(a.iters + 1):
+            for p in plans:
+                p.upload(ob)
+            for c in ctxs[:world]:
+                c.sync()
+            for p in plans:
+                p.run()
+            paths = [p.download()[0][0] for p in plans]
+            rep = plans[0].report()
+            if it > 0:
+                best = rep.first_pass_ms if best is None else min(best, rep.first_pass_ms)
+        if base_path is None:
+            base_path = paths[0]
+        same = all(np.array_equal(x, base_path) for x in paths)
+        out[world] = {"first_pass_ms": best, "decode_ms": rep.decode_ms, "paths_equal_1gpu": bool(same)}
+        print(f"world={world}: first pass {best:.3f} ms ({(a.T - 1) * a.K * a.K * 4 / best / 1e6:.0f} GB/s algorithmic), "
+              f"whole decode {rep.decode_ms:.3f} ms, same path as 1 GPU: {same}", flush=True)
+        for p in plans:
+            p.close()
+        world *= 2
+    print(json.dumps({"K": a.K, "T": a.T, "N": a.N, "results": out}))
+
+
+if __name__ == "__main__":
+    main()
