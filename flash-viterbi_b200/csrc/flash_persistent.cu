@@ -201,14 +201,16 @@ __device__ __forceinline__ void publish_delta(unsigned long long *xch, int i, fl
     asm volatile("st.global.u64 [%0], %1;" ::"l"(xch + i), "l"(w) : "memory");
 }
 __device__ __forceinline__ unsigned step_tag(const PersistArgs &a, int step) { return (a.epoch << 16) | (unsigned)step; }
-// Sharded form: the word goes to every GPU.  The release orders this thread's earlier stores to
-// the same GPU (its backpointer entry) before the tagged word, which is what the final hand-shake
-// of the pass relies on; during the pass nothing depends on that order.
-__device__ __forceinline__ void publish_delta_peers(const PersistArgs &a, int parity, int i, float v, int step)
+// Sharded form: the word goes to every GPU (plain 64-bit stores; the tag makes each one self-
+// validating).  Only the LAST step of a pass needs ordering: the final hand-shake promises that
+// once a GPU's last delta word is visible, so are its backpointer entries, hence the system-scope
+// fence between them there.
+__device__ __forceinline__ void publish_delta_peers(const PersistArgs &a, int parity, int i, float v, int step, bool last)
 {
     const unsigned long long w = ((unsigned long long)step_tag(a, step) << 32) | (unsigned long long)__float_as_uint(v);
+    if (last) __threadfence_system();
     for (int r = 0; r < a.npeer; ++r)
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.xch_peer[r] + (size_t)parity * a.Kp + i), "l"(w) : "memory");
+        asm volatile("st.global.u64 [%0], %1;" ::"l"(a.xch_peer[r] + (size_t)parity * a.Kp + i), "l"(w) : "memory");
 }
 
 // Stage delta_{s-1} in shared memory: from the plain start vector for s == 1, else from the
@@ -586,7 +588,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                     if (keep)
                         for (int r = 0; r < a.npeer; ++r)
                             psi_store(a.psi_peer[r], a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i0, r0.k);
-                    publish_delta_peers(a, s & 1, i0, r0.x, s);
+                    publish_delta_peers(a, s & 1, i0, r0.x, s, last_step);
                 } else {
                     publish_delta(xout, i0, r0.x, (int)step_tag(a, s));
                     if (last_step) a.d_final[i0] = r0.x;
@@ -600,7 +602,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                         if (keep)
                             for (int r = 0; r < a.npeer; ++r)
                                 psi_store(a.psi_peer[r], a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i1, r1.k);
-                        publish_delta_peers(a, s & 1, i1, r1.x, s);
+                        publish_delta_peers(a, s & 1, i1, r1.x, s, last_step);
                     } else {
                         publish_delta(xout, i1, r1.x, (int)step_tag(a, s));
                         if (last_step) a.d_final[i1] = r1.x;
