@@ -712,7 +712,11 @@ int persistent_pass(flashv_plan *p, const Pass &pass)
     a.psi = p->d_psi, a.psi16 = p->psi16;
     a.epoch = (++p->run_epoch) & 0xffffu;
     if (a.epoch == 0) a.epoch = (++p->run_epoch) & 0xffffu;  // tag 0 is what a fresh buffer holds
-    if (p->shard_world > 1) {
+    // Only the plan's first pass is sharded (the N-way pass, or the root task): it is the one long
+    // single-vector pass, and it is the only time every GPU is known to be in lock-step.  Later
+    // single-vector passes are a step or two long and run locally, so no GPU ever writes into a
+    // peer's backpointer store while that peer may still be walking it.
+    if (p->shard_world > 1 && &pass == &p->passes[0]) {
         // state-sharded: this GPU owns the columns [shard_c0, shard_c0 + shard_ncol) and publishes
         // into every GPU's buffers (same offsets in every plan: identical plan parameters)
         if (a.nsteps >= 65536) {

@@ -108,10 +108,10 @@ int flashv_plan_report(flashv_plan *plan, flashv_report *report);            /* 
 /* ---- state sharding of one huge K across the GPUs of a box -------------------- */
 /* Every rank holds the full model and an identical FLASH plan (batch 1, persistent engine).  After
  * flashv_plan_shard_init(plan, rank, world) a rank computes only its slice of destination states
- * in every single-vector pass (the N-way first pass of F:126-202); each step it stores its slice
+ * in the plan's first pass (the N-way pass of F:126-202, or the root task); each step it stores its slice
  * of delta and of the backpointer row into the buffers of ALL ranks with in-kernel peer stores over
- * NVLink and polls only its own copy — the per-step all-gather, with no host or NCCL call.  The tree
- * levels then run replicated.  Ranks exchange their buffers once: raw pointers inside one process
+ * NVLink and polls only its own copy — the per-step all-gather, with no host or NCCL call.  Everything
+ * after that pass (the tree levels) runs replicated on every rank.  Ranks exchange their buffers once: raw pointers inside one process
  * (set_peer enables peer access), cudaIpc handles between processes (128 bytes per rank, e.g. through
  * torch.distributed.all_gather).  All ranks must call flashv_plan_run together (barrier first). */
 int flashv_plan_shard_init(flashv_plan *plan, int rank, int world);
