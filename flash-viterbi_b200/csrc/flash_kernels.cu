@@ -8,6 +8,10 @@
 // an HBM store and one thread per vector walks it backwards afterwards; composing T2 forward and
 // walking psi backward give the same state by construction (T2_j[i] = T2_{j-1}[psi_j[i]]).
 //   F: = /root/reference/src/FLASH_Viterbi_multithread.c
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "flashv_internal.h"
 #include "trellis_common.cuh"
 
@@ -182,6 +186,40 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
     }
 }
 
+// ---- the last step of a task needs one column ---------------------------------------------------
+// nvviter() ends with Ans[mid] = T2[cur][Ans[R]] (F:248, F:261): of the K values the last step
+// computes, only the backpointer of destination state Ans[R] is ever read (delta of the last step
+// is only needed by full-range passes, F:249-259).  So a task's last step is K updates, not K^2 —
+// and half of all tasks are one step long.  One warp per vector; same estimate / window / exact
+// logic as every other kernel.
+__global__ void __launch_bounds__(128) k_flash_last_column(const StepArgs a, int v_begin, const int32_t *__restrict__ ans)
+{
+    const int lane = threadIdx.x & 31;
+    const int v = v_begin + blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (v >= a.nact) return;  // a.nact: one past the last vector on its final step
+    const VecDesc vd = a.vecs[v];
+    const int j = vd.L + a.s;  // == vd.R
+    const int e = ans[(size_t)vd.seq * a.T + vd.R];
+    if (e < 0 || e >= a.K) return;
+    const float tmp = __ldg(a.LBf + (size_t)a.ob[(size_t)vd.seq * a.T + j] * a.Kp + e);  // F:233
+    const float *col = a.hiT + (size_t)e * a.Kp;
+    const float *delta = a.din + (size_t)v * a.Kp;
+    const float4 *col4 = reinterpret_cast<const float4 *>(col);
+    const float4 *d4 = reinterpret_cast<const float4 *>(delta);
+    float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 4
+    for (int t = lane; t < (a.Kp >> 2); t += 32) {
+        const float4 h = __ldg(col4 + t);
+        const float4 d = __ldg(d4 + t);
+        cm[0] = fmaxf(cm[0], __fadd_rn(__fadd_rn(tmp, d.x), h.x));
+        cm[1] = fmaxf(cm[1], __fadd_rn(__fadd_rn(tmp, d.y), h.y));
+        cm[2] = fmaxf(cm[2], __fadd_rn(__fadd_rn(tmp, d.z), h.z));
+        cm[3] = fmaxf(cm[3], __fadd_rn(__fadd_rn(tmp, d.w), h.w));
+    }
+    const Best b = resolve_column(cm, tmp, col, delta, a.LAd, a.K, a.Kp, e, lane);
+    if (lane == 0) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * a.K + e, b.k);
+}
+
 // ---- many vectors over a small table: one CTA walks QB vectors through ALL their steps ------
 // For batches of sequences (BASELINE config 4: 8192 sequences, K=512) a launch per step would
 // re-stage delta through HBM every step.  Here delta of a group of QB vectors ping-pongs between
@@ -203,28 +241,43 @@ struct GroupArgs {
     int psi16;
 };
 
-// Per step the CTA works in two phases separated by a barrier:
+// Per step the CTA works in three phases separated by barriers:
 //   A  warps sweep the columns (RI at a time) and keep only the running maxima of the estimates;
 //      per (column, vector) pair they leave a 8-byte record: the largest estimate and the one
 //      chain (lane, component) whose maximum lies inside the window (or "ambiguous");
 //   B  one THREAD per pair re-reads that chain (Kp/128 elements), evaluates the candidates exactly
 //      and writes delta', the backpointer and, at a vector's last step, the final delta.  Several
 //      pairs per thread are in flight at once, so the two dependent memory round trips of a
-//      resolution are paid once per batch, not once per pair.
+//      resolution are paid once per batch, not once per pair.  Ambiguous pairs (several chains
+//      inside the window: about 1 % of the pairs at |delta| ~ 10^3) go to a list instead;
+//   C  one WARP per listed pair scans the whole column with all its loads in flight.
+// A vector's last step (unless the pass is full-range) needs one column only — Ans[mid] =
+// T2[cur][Ans[R]], F:248/F:261 — so there warp q resolves column Ans[R] of vector q and phases A-C
+// are skipped.
 struct PairRec {
     float top;
     int chain;  // lane | component << 8, or -1: ambiguous (several chains inside the window)
 };
 
-template <int QB, int RI, int NWARP>
-__global__ void __launch_bounds__(NWARP * 32) k_flash_group_pass(const GroupArgs a)
+constexpr int GROUP_LIST_CAP = 2048;  // ambiguous pairs per step handled by phase C (more: resolved in place)
+
+__host__ __device__ inline size_t group_smem_bytes(int QB, int Kp)
 {
-    extern __shared__ float4 sgroup4[];  // delta [2][QB][Kp] floats, then PairRec [QB][Kp], then VecDesc[QB]
+    return (size_t)2 * QB * Kp * sizeof(float) + (size_t)QB * Kp * sizeof(PairRec) + (size_t)QB * sizeof(VecDesc) +
+           (size_t)(GROUP_LIST_CAP + 4) * sizeof(int);
+}
+
+template <int QB, int RI, int NWARP>
+__global__ void __launch_bounds__(NWARP * 32, 16 / NWARP) k_flash_group_pass(const GroupArgs a)
+{
+    extern __shared__ float4 sgroup4[];  // delta [2][QB][Kp] floats, PairRec [QB][Kp], VecDesc[QB], list
     constexpr int NT = NWARP * 32;
     const int Kp4 = a.Kp >> 2;
     float *sbuf = reinterpret_cast<float *>(sgroup4);
     PairRec *srec = reinterpret_cast<PairRec *>(sbuf + (size_t)2 * QB * a.Kp);
     VecDesc *svd = reinterpret_cast<VecDesc *>(srec + (size_t)QB * a.Kp);
+    int *scount = reinterpret_cast<int *>(svd + QB);
+    int *slist = scount + 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ngroups = (a.nvec + QB - 1) / QB;
     const int chain_len = a.Kp >> 7;
@@ -240,6 +293,7 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_group_pass(const GroupArgs
         int gsteps = 0;
 #pragma unroll
         for (int q = 0; q < QB; ++q) gsteps = max(gsteps, svd[q].R - svd[q].L);
+        const bool one_column_end = !(svd[0].flags & VEC_FULL_RANGE);  // flags are per pass
         // start vectors, F:142 / F:220
 #pragma unroll
         for (int q = 0; q < QB; ++q) {
@@ -268,6 +322,37 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_group_pass(const GroupArgs
                 const VecDesc d = svd[q];
                 tmp_row[q] = a.LBf + (size_t)a.ob[(size_t)d.seq * a.T + min(d.L + s, d.R)] * a.Kp;  // F:167
             }
+            if (s == gsteps && one_column_end) {
+                // ---- the group's last step: one column per vector -------------------------------
+                for (int q = warp; q < QB; q += NWARP) {
+                    const VecDesc d = svd[q];
+                    if (d.R - d.L != s) continue;  // finished earlier (or padding)
+                    const int e = a.ans[(size_t)d.seq * a.T + d.R];
+                    if (e < 0 || e >= a.K) continue;
+                    float tmp = 0.f;
+#pragma unroll
+                    for (int qq = 0; qq < QB; ++qq)
+                        if (qq == q) tmp = __ldg(tmp_row[qq] + e);
+                    const float *col = a.hiT + (size_t)e * a.Kp;
+                    const float *delta = sin + (size_t)q * a.Kp;
+                    const float4 *col4 = reinterpret_cast<const float4 *>(col);
+                    const float4 *d4 = reinterpret_cast<const float4 *>(delta);
+                    float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 4
+                    for (int t = lane; t < Kp4; t += 32) {
+                        const float4 h = __ldg(col4 + t);
+                        const float4 dv = d4[t];
+                        cm[0] = fmaxf(cm[0], __fadd_rn(__fadd_rn(tmp, dv.x), h.x));
+                        cm[1] = fmaxf(cm[1], __fadd_rn(__fadd_rn(tmp, dv.y), h.y));
+                        cm[2] = fmaxf(cm[2], __fadd_rn(__fadd_rn(tmp, dv.z), h.z));
+                        cm[3] = fmaxf(cm[3], __fadd_rn(__fadd_rn(tmp, dv.w), h.w));
+                    }
+                    const Best b = resolve_column(cm, tmp, col, delta, a.LAd, a.K, a.Kp, e, lane);
+                    if (lane == 0) psi_store(a.psi, a.psi16, (size_t)(d.psi_row + (d.R - d.mid - 1)) * a.K + e, b.k);
+                }
+                break;  // the loop over groups starts with a barrier
+            }
+            if (tid == 0) *scount = 0;  // readers of the previous step are behind that step's last barrier
             // ---- phase A ------------------------------------------------------------------
             for (int ibase = warp * RI; ibase < a.K; ibase += NWARP * RI) {
                 const float4 *col4[RI];
@@ -310,13 +395,36 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_group_pass(const GroupArgs
                 }
             }
             __syncthreads();
+            // the result of one pair: delta', backpointer, final delta
+            auto emit = [&](int q, int i, Best b) {
+                if (!(b.x > -FLT_MAX)) b.x = -FLT_MAX, b.k = -1;
+                const VecDesc d = svd[q];
+                if (s > d.R - d.L) return;  // this vector has finished
+                const int j = d.L + s;
+                sout[(size_t)q * a.Kp + i] = b.x;
+                if (j >= d.mid + 1)  // F:242
+                    psi_store(a.psi, a.psi16, (size_t)(d.psi_row + (j - d.mid - 1)) * a.K + i, b.k);
+                if (j == d.R) a.dfinal[(size_t)(v0 + q) * a.Kp + i] = b.x;
+            };
+            // every source state of column i whose estimate is inside the window, by one thread
+            auto scan_serial = [&](int q, int i, float tmpv, int thr) {
+                Best b{-FLT_MAX, 0x7fffffff};
+                for (int k = 0; k < a.K; ++k) {
+                    const float pre = __fadd_rn(tmpv, sin[(size_t)q * a.Kp + k]);
+                    if (ford(__fadd_rn(pre, __ldg(a.hiT + (size_t)i * a.Kp + k))) >= thr) {
+                        const float x = exact_cand(pre, __ldg(a.LAd + (size_t)k * a.K + i));
+                        if (x > -FLT_MAX) best_take(b, x, k);
+                    }
+                }
+                return b;
+            };
             // ---- phase B ------------------------------------------------------------------
             constexpr int UP = 4;  // pairs in flight per thread
             const int npairs = QB * a.K;
             for (int p0 = tid; p0 < npairs; p0 += NT * UP) {
                 int pi[UP], pq[UP], pw[UP], pc[UP], thr[UP];
                 float ptmp[UP];
-                bool ok[UP], simple[UP];
+                bool ok[UP], simple[UP], listed[UP];
                 Best best[UP];
 #pragma unroll
                 for (int e = 0; e < UP; ++e) {
@@ -327,6 +435,7 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_group_pass(const GroupArgs
                     const PairRec rec = srec[(size_t)pq[e] * a.Kp + pi[e]];
                     thr[e] = ford(rec.top) - WINDOW_STEPS;
                     simple[e] = ok[e] && rec.chain >= 0 && rec.top > -FLT_MAX;
+                    listed[e] = ok[e] && rec.chain < 0 && rec.top > -FLT_MAX;
                     pw[e] = rec.chain & 0xff, pc[e] = (rec.chain >> 8) & 3;
                     best[e] = Best{-FLT_MAX, 0x7fffffff};  // a dead column (top <= -FLT_MAX) keeps this
                 }
@@ -367,27 +476,46 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_group_pass(const GroupArgs
 #pragma unroll
                 for (int e = 0; e < UP; ++e) {
                     if (!ok[e]) continue;
-                    const PairRec rec = srec[(size_t)pq[e] * a.Kp + pi[e]];
-                    if (rec.chain < 0 && rec.top > -FLT_MAX) {
-                        // ambiguous: every source state whose estimate is inside the window
-                        for (int k = 0; k < a.K; ++k) {
-                            const float pre = __fadd_rn(ptmp[e], sin[(size_t)pq[e] * a.Kp + k]);
-                            if (ford(__fadd_rn(pre, __ldg(a.hiT + (size_t)pi[e] * a.Kp + k))) >= thr[e]) {
-                                const float x = exact_cand(pre, __ldg(a.LAd + (size_t)k * a.K + pi[e]));
-                                if (x > -FLT_MAX) best_take(best[e], x, k);
-                            }
+                    if (listed[e]) {
+                        const int slot = atomicAdd(scount, 1);
+                        if (slot < GROUP_LIST_CAP) {
+                            slist[slot] = pq[e] << 24 | pi[e];
+                            continue;
+                        }
+                        best[e] = scan_serial(pq[e], pi[e], ptmp[e], thr[e]);  // list full
+                    }
+                    emit(pq[e], pi[e], best[e]);
+                }
+            }
+            __syncthreads();
+            // ---- phase C ------------------------------------------------------------------
+            const int nlisted = min(*scount, GROUP_LIST_CAP);
+            for (int e = warp; e < nlisted; e += NWARP) {
+                const int q = slist[e] >> 24, i = slist[e] & 0xffffff;
+                const int thr = ford(srec[(size_t)q * a.Kp + i].top) - WINDOW_STEPS;
+                float tmpv = 0.f;
+#pragma unroll
+                for (int qq = 0; qq < QB; ++qq)
+                    if (qq == q) tmpv = __ldg(tmp_row[qq] + i);
+                const float4 *col4 = reinterpret_cast<const float4 *>(a.hiT + (size_t)i * a.Kp);
+                Best b{-FLT_MAX, 0x7fffffff};
+#pragma unroll 4
+                for (int t = lane; t < Kp4; t += 32) {
+                    const float4 h = __ldg(col4 + t);
+                    const float4 dv = sin4[q * Kp4 + t];
+                    const float hh[4] = {h.x, h.y, h.z, h.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int k = 4 * t + c;
+                        const float pre = __fadd_rn(tmpv, dd[c]);
+                        if (k < a.K && ford(__fadd_rn(pre, hh[c])) >= thr) {
+                            const float x = exact_cand(pre, __ldg(a.LAd + (size_t)k * a.K + i));
+                            if (x > -FLT_MAX) best_take(b, x, k);
                         }
                     }
-                    Best b = best[e];
-                    if (!(b.x > -FLT_MAX)) b.x = -FLT_MAX, b.k = -1;
-                    const VecDesc d = svd[pq[e]];
-                    if (s > d.R - d.L) continue;  // this vector has finished
-                    const int i = pi[e], j = d.L + s;
-                    sout[(size_t)pq[e] * a.Kp + i] = b.x;
-                    if (j >= d.mid + 1)  // F:242
-                        psi_store(a.psi, a.psi16, (size_t)(d.psi_row + (j - d.mid - 1)) * a.K + i, b.k);
-                    if (j == d.R) a.dfinal[(size_t)(v0 + pq[e]) * a.Kp + i] = b.x;
                 }
+                b = warp_best(b);
+                if (lane == 0) emit(q, i, b);
             }
             __syncthreads();
             cur ^= 1;
@@ -533,7 +661,7 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
     const float *final_delta = d0;
     const bool persistent = p->engine == FLASHV_ENGINE_PERSISTENT && pass.nvec == 1;
     // many vectors over a table small enough that two delta sets of 8 vectors fit in shared memory
-    const size_t group_smem = (size_t)4 * 8 * Kp * sizeof(float) + 8 * sizeof(VecDesc);  // 2 delta sets + 8-byte pair records
+    const size_t group_smem = group_smem_bytes(8, Kp);
     const bool grouped = p->engine != FLASHV_ENGINE_STEP && pass.nvec >= 2 * ctx->sm_count && group_smem <= 200 * 1024;
     if (!grouped) {  // the group kernel builds its start vectors itself
         dim3 ig((K + 255) / 256, pass.nvec < 65535 ? pass.nvec : 65535);
@@ -547,11 +675,20 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
         g.vecs = vecs, g.nvec = pass.nvec, g.ob = p->d_ob, g.ans = p->d_ans, g.T = T;
         g.dfinal = d1, g.psi = p->d_psi, g.psi16 = p->psi16;
         const size_t smem = group_smem;
-        FV_CUDA(cudaFuncSetAttribute(k_flash_group_pass<8, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        int grid = ctx->sm_count;  // 512 threads x 128 registers: one CTA per SM, looping over groups
         const int ngroups = (pass.nvec + 7) / 8;
-        if (grid > ngroups) grid = ngroups;
-        k_flash_group_pass<8, 2, 16><<<grid, 512, smem, st>>>(g);
+        // two 8-warp CTAs per SM when their buffers fit (one resolves while the other streams), else
+        // one 16-warp CTA; either way 128 registers per thread, looping over groups
+        static const int force_warps = getenv("FLASHV_GROUP_WARPS") ? atoi(getenv("FLASHV_GROUP_WARPS")) : 0;
+        const bool two = force_warps ? force_warps == 8 : 2 * (smem + 1024) <= (size_t)ctx->smem_optin;
+        if (two) {
+            FV_CUDA(cudaFuncSetAttribute(k_flash_group_pass<8, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = std::min(2 * ctx->sm_count, ngroups);
+            k_flash_group_pass<8, 2, 8><<<grid, 256, smem, st>>>(g);
+        } else {
+            FV_CUDA(cudaFuncSetAttribute(k_flash_group_pass<8, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = std::min(ctx->sm_count, ngroups);
+            k_flash_group_pass<8, 2, 16><<<grid, 512, smem, st>>>(g);
+        }
         FV_CUDA(cudaGetLastError());
         ++p->launches;
         final_delta = d1;
@@ -563,11 +700,24 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
         for (int s = 1; s <= pass.max_steps; ++s) {
             StepArgs a;
             a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = K, a.Kp = Kp;
-            a.vecs = vecs, a.nact = pass.nactive[s], a.s = s;
+            a.vecs = vecs, a.s = s;
             a.din = (s & 1) ? d0 : d1, a.dout = (s & 1) ? d1 : d0;
             a.ob = p->d_ob, a.T = T, a.psi = p->d_psi, a.psi16 = p->psi16;
-            FV_CUDA(dispatch_step(a, a.nact, ctx->sm_count, st));
-            ++p->launches;
+            // vectors are sorted longest first: [0, n_cont) go on after this step, [n_cont, n_act) are
+            // on their last step and (unless the pass is full-range) need a single column
+            const int n_act = pass.nactive[s];
+            const int n_cont = pass.full_range ? n_act : pass.nactive[s + 1];
+            if (n_cont > 0) {
+                a.nact = n_cont;
+                FV_CUDA(dispatch_step(a, n_cont, ctx->sm_count, st));
+                ++p->launches;
+            }
+            if (n_act > n_cont) {
+                a.nact = n_act;
+                k_flash_last_column<<<(n_act - n_cont + 3) / 4, 128, 0, st>>>(a, n_cont, p->d_ans);
+                FV_CUDA(cudaGetLastError());
+                ++p->launches;
+            }
         }
         final_delta = (pass.max_steps & 1) ? d1 : d0;
     }

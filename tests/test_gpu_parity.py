@@ -199,6 +199,33 @@ def test_large_batch_group_engine(fv, oracle_mod, gpu_ctx):
     model.close()
 
 
+def test_config4_shape_group_engine(fv, oracle_mod, gpu_ctx):
+    """BASELINE config 4's shape at a reduced batch and length (K=512, many sequences, long enough
+    that |delta| reaches 10^3 and several chains fall inside the window): the group engine
+    (phases A/B/C and the one-column last step) must equal the per-step engine on every sequence
+    and the oracle on a sample."""
+    K, M, T, N = 512, 50, 200, 12
+    A, B, Pi = random_hmm(K, M, 0.112, 81)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    rng = np.random.RandomState(81)
+    obs = rng.randint(0, M, (309, T)).astype(np.int32)
+    got = {}
+    for eng in (fv.ENGINE_PERSISTENT, fv.ENGINE_STEP):
+        plan = fv.Plan(model, T, N, obs.shape[0], 0, eng)
+        plan.upload(obs)
+        plan.run()
+        got[eng] = plan.download()
+        plan.close()
+    assert np.array_equal(got[fv.ENGINE_PERSISTENT][0], got[fv.ENGINE_STEP][0])
+    assert np.array_equal(_bits(got[fv.ENGINE_PERSISTENT][1]), _bits(got[fv.ENGINE_STEP][1]))
+    for b in (0, 77, 308):
+        want, wscore, _ = om.flash(obs[b], N)
+        assert np.array_equal(got[fv.ENGINE_PERSISTENT][0][b], want), b
+        assert _bits(got[fv.ENGINE_PERSISTENT][1][b]) == _bits(wscore)
+    model.close()
+
+
 def test_wide_model_multi_round(fv, oracle_mod, gpu_ctx):
     """K large enough that a persistent CTA owns more columns than one round (28) and a chain is
     longer than a warp (K > 4096): the general paths of the window scan."""
