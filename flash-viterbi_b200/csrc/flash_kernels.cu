@@ -220,309 +220,6 @@ __global__ void __launch_bounds__(128) k_flash_last_column(const StepArgs a, int
     if (lane == 0) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * a.K + e, b.k);
 }
 
-// ---- many vectors over a small table: one CTA walks QB vectors through ALL their steps ------
-// For batches of sequences (BASELINE config 4: 8192 sequences, K=512) a launch per step would
-// re-stage delta through HBM every step.  Here delta of a group of QB vectors ping-pongs between
-// two shared-memory buffers for the whole pass, the CTA computes every destination column of
-// every step itself (warps take RI columns at a time), and only backpointer rows and the final
-// delta go to HBM.  No inter-CTA dependency at all: groups are independent units of work.
-struct GroupArgs {
-    const float *hiT;
-    const double *LAd, *LBd, *LPi;
-    const float *LBf;
-    int K, Kp;
-    const VecDesc *vecs;
-    int nvec;
-    const int32_t *ob;
-    const int32_t *ans;
-    int T;
-    float *dfinal;  // [nvec][Kp] delta after each vector's last step (full-range vectors read it)
-    void *psi;
-    int psi16;
-};
-
-// Per step the CTA works in three phases separated by barriers:
-//   A  warps sweep the columns (RI at a time) and keep only the running maxima of the estimates;
-//      per (column, vector) pair they leave a 8-byte record: the largest estimate and the one
-//      chain (lane, component) whose maximum lies inside the window (or "ambiguous");
-//   B  one THREAD per pair re-reads that chain (Kp/128 elements), evaluates the candidates exactly
-//      and writes delta', the backpointer and, at a vector's last step, the final delta.  Several
-//      pairs per thread are in flight at once, so the two dependent memory round trips of a
-//      resolution are paid once per batch, not once per pair.  Ambiguous pairs (several chains
-//      inside the window: about 1 % of the pairs at |delta| ~ 10^3) go to a list instead;
-//   C  one WARP per listed pair scans the whole column with all its loads in flight.
-// A vector's last step (unless the pass is full-range) needs one column only — Ans[mid] =
-// T2[cur][Ans[R]], F:248/F:261 — so there warp q resolves column Ans[R] of vector q and phases A-C
-// are skipped.
-struct PairRec {
-    float top;
-    int chain;  // lane | component << 8, or -1: ambiguous (several chains inside the window)
-};
-
-constexpr int GROUP_LIST_CAP = 2048;  // ambiguous pairs per step handled by phase C (more: resolved in place)
-
-__host__ __device__ inline size_t group_smem_bytes(int QB, int Kp)
-{
-    return (size_t)2 * QB * Kp * sizeof(float) + (size_t)QB * Kp * sizeof(PairRec) + (size_t)QB * sizeof(VecDesc) +
-           (size_t)(GROUP_LIST_CAP + 4) * sizeof(int);
-}
-
-template <int QB, int RI, int NWARP>
-__global__ void __launch_bounds__(NWARP * 32, 16 / NWARP) k_flash_group_pass(const GroupArgs a)
-{
-    extern __shared__ float4 sgroup4[];  // delta [2][QB][Kp] floats, PairRec [QB][Kp], VecDesc[QB], list
-    constexpr int NT = NWARP * 32;
-    const int Kp4 = a.Kp >> 2;
-    float *sbuf = reinterpret_cast<float *>(sgroup4);
-    PairRec *srec = reinterpret_cast<PairRec *>(sbuf + (size_t)2 * QB * a.Kp);
-    VecDesc *svd = reinterpret_cast<VecDesc *>(srec + (size_t)QB * a.Kp);
-    int *scount = reinterpret_cast<int *>(svd + QB);
-    int *slist = scount + 4;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ngroups = (a.nvec + QB - 1) / QB;
-    const int chain_len = a.Kp >> 7;
-    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        const int v0 = g * QB;
-        __syncthreads();  // previous group done with the buffers
-        if (tid < QB) {
-            VecDesc d = a.vecs[min(v0 + tid, a.nvec - 1)];
-            if (v0 + tid >= a.nvec) d.R = d.L;  // padding vector: no steps
-            svd[tid] = d;
-        }
-        __syncthreads();
-        int gsteps = 0;
-#pragma unroll
-        for (int q = 0; q < QB; ++q) gsteps = max(gsteps, svd[q].R - svd[q].L);
-        const bool one_column_end = !(svd[0].flags & VEC_FULL_RANGE);  // flags are per pass
-        // start vectors, F:142 / F:220
-#pragma unroll
-        for (int q = 0; q < QB; ++q) {
-            const VecDesc d = svd[q];
-            const int prev = d.L == 0 ? -1 : a.ans[(size_t)d.seq * a.T + d.L - 1];
-            const int o = a.ob[(size_t)d.seq * a.T + d.L];
-            for (int i = tid; i < a.Kp; i += NT) {
-                float v = 0.f;  // padding lanes stay finite (hiT pads with -inf)
-                if (i < a.K) {
-                    const double head = prev < 0 ? a.LPi[i] : a.LAd[(size_t)prev * a.K + i];
-                    v = __double2float_rn(__dadd_rn(head, a.LBd[(size_t)o * a.K + i]));
-                }
-                sbuf[(size_t)q * a.Kp + i] = v;
-                sbuf[(size_t)(QB + q) * a.Kp + i] = 0.f;
-            }
-        }
-        __syncthreads();
-        int cur = 0;
-        for (int s = 1; s <= gsteps; ++s) {
-            const float *sin = sbuf + (size_t)cur * QB * a.Kp;
-            float *sout = sbuf + (size_t)(cur ^ 1) * QB * a.Kp;
-            const float4 *sin4 = reinterpret_cast<const float4 *>(sin);
-            const float *tmp_row[QB];
-#pragma unroll
-            for (int q = 0; q < QB; ++q) {
-                const VecDesc d = svd[q];
-                tmp_row[q] = a.LBf + (size_t)a.ob[(size_t)d.seq * a.T + min(d.L + s, d.R)] * a.Kp;  // F:167
-            }
-            if (s == gsteps && one_column_end) {
-                // ---- the group's last step: one column per vector -------------------------------
-                for (int q = warp; q < QB; q += NWARP) {
-                    const VecDesc d = svd[q];
-                    if (d.R - d.L != s) continue;  // finished earlier (or padding)
-                    const int e = a.ans[(size_t)d.seq * a.T + d.R];
-                    if (e < 0 || e >= a.K) continue;
-                    float tmp = 0.f;
-#pragma unroll
-                    for (int qq = 0; qq < QB; ++qq)
-                        if (qq == q) tmp = __ldg(tmp_row[qq] + e);
-                    const float *col = a.hiT + (size_t)e * a.Kp;
-                    const float *delta = sin + (size_t)q * a.Kp;
-                    const float4 *col4 = reinterpret_cast<const float4 *>(col);
-                    const float4 *d4 = reinterpret_cast<const float4 *>(delta);
-                    float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 4
-                    for (int t = lane; t < Kp4; t += 32) {
-                        const float4 h = __ldg(col4 + t);
-                        const float4 dv = d4[t];
-                        cm[0] = fmaxf(cm[0], __fadd_rn(__fadd_rn(tmp, dv.x), h.x));
-                        cm[1] = fmaxf(cm[1], __fadd_rn(__fadd_rn(tmp, dv.y), h.y));
-                        cm[2] = fmaxf(cm[2], __fadd_rn(__fadd_rn(tmp, dv.z), h.z));
-                        cm[3] = fmaxf(cm[3], __fadd_rn(__fadd_rn(tmp, dv.w), h.w));
-                    }
-                    const Best b = resolve_column(cm, tmp, col, delta, a.LAd, a.K, a.Kp, e, lane);
-                    if (lane == 0) psi_store(a.psi, a.psi16, (size_t)(d.psi_row + (d.R - d.mid - 1)) * a.K + e, b.k);
-                }
-                break;  // the loop over groups starts with a barrier
-            }
-            if (tid == 0) *scount = 0;  // readers of the previous step are behind that step's last barrier
-            // ---- phase A ------------------------------------------------------------------
-            for (int ibase = warp * RI; ibase < a.K; ibase += NWARP * RI) {
-                const float4 *col4[RI];
-                float tmp[RI][QB];
-                float cm[RI][QB][4];
-#pragma unroll
-                for (int r = 0; r < RI; ++r) {
-                    const int ci = min(ibase + r, a.K - 1);
-                    col4[r] = reinterpret_cast<const float4 *>(a.hiT + (size_t)ci * a.Kp);
-#pragma unroll
-                    for (int q = 0; q < QB; ++q) {
-                        tmp[r][q] = __ldg(tmp_row[q] + ci);
-                        cm[r][q][0] = cm[r][q][1] = cm[r][q][2] = cm[r][q][3] = -INFINITY;
-                    }
-                }
-                tile_accumulate<QB, RI>(cm, tmp, col4, sin4, Kp4, lane);
-#pragma unroll
-                for (int r = 0; r < RI; ++r) {
-                    if (ibase + r >= a.K) continue;  // warp-uniform: the clamped duplicate column
-#pragma unroll
-                    for (int q = 0; q < QB; ++q) {
-                        const float lm = fmaxf(fmaxf(cm[r][q][0], cm[r][q][1]), fmaxf(cm[r][q][2], cm[r][q][3]));
-                        const float top = warp_max(lm);
-                        const int thr = ford(top) - WINDOW_STEPS;
-                        const unsigned hit = __ballot_sync(FULL_MASK, ford(lm) >= thr);
-                        // the lanes inside the window say which of their components are
-                        int comps = 0;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) comps |= (ford(cm[r][q][c]) >= thr) << c;
-                        const int w = __ffs(hit) - 1;
-                        const int wc = __shfl_sync(FULL_MASK, comps, w < 0 ? 0 : w);
-                        const bool single = __popc(hit) == 1 && __popc(wc) == 1;
-                        if (lane == 0) {
-                            PairRec rec;
-                            rec.top = top;
-                            rec.chain = single ? (w | (__ffs(wc) - 1) << 8) : -1;
-                            srec[(size_t)q * a.Kp + ibase + r] = rec;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            // the result of one pair: delta', backpointer, final delta
-            auto emit = [&](int q, int i, Best b) {
-                if (!(b.x > -FLT_MAX)) b.x = -FLT_MAX, b.k = -1;
-                const VecDesc d = svd[q];
-                if (s > d.R - d.L) return;  // this vector has finished
-                const int j = d.L + s;
-                sout[(size_t)q * a.Kp + i] = b.x;
-                if (j >= d.mid + 1)  // F:242
-                    psi_store(a.psi, a.psi16, (size_t)(d.psi_row + (j - d.mid - 1)) * a.K + i, b.k);
-                if (j == d.R) a.dfinal[(size_t)(v0 + q) * a.Kp + i] = b.x;
-            };
-            // every source state of column i whose estimate is inside the window, by one thread
-            auto scan_serial = [&](int q, int i, float tmpv, int thr) {
-                Best b{-FLT_MAX, 0x7fffffff};
-                for (int k = 0; k < a.K; ++k) {
-                    const float pre = __fadd_rn(tmpv, sin[(size_t)q * a.Kp + k]);
-                    if (ford(__fadd_rn(pre, __ldg(a.hiT + (size_t)i * a.Kp + k))) >= thr) {
-                        const float x = exact_cand(pre, __ldg(a.LAd + (size_t)k * a.K + i));
-                        if (x > -FLT_MAX) best_take(b, x, k);
-                    }
-                }
-                return b;
-            };
-            // ---- phase B ------------------------------------------------------------------
-            constexpr int UP = 4;  // pairs in flight per thread
-            const int npairs = QB * a.K;
-            for (int p0 = tid; p0 < npairs; p0 += NT * UP) {
-                int pi[UP], pq[UP], pw[UP], pc[UP], thr[UP];
-                float ptmp[UP];
-                bool ok[UP], simple[UP], listed[UP];
-                Best best[UP];
-#pragma unroll
-                for (int e = 0; e < UP; ++e) {
-                    const int p = p0 + e * NT;
-                    ok[e] = p < npairs;
-                    pq[e] = ok[e] ? p / a.K : 0;
-                    pi[e] = ok[e] ? p - pq[e] * a.K : 0;
-                    const PairRec rec = srec[(size_t)pq[e] * a.Kp + pi[e]];
-                    thr[e] = ford(rec.top) - WINDOW_STEPS;
-                    simple[e] = ok[e] && rec.chain >= 0 && rec.top > -FLT_MAX;
-                    listed[e] = ok[e] && rec.chain < 0 && rec.top > -FLT_MAX;
-                    pw[e] = rec.chain & 0xff, pc[e] = (rec.chain >> 8) & 3;
-                    best[e] = Best{-FLT_MAX, 0x7fffffff};  // a dead column (top <= -FLT_MAX) keeps this
-                }
-#pragma unroll
-                for (int e = 0; e < UP; ++e) {  // tmp of the pair's own vector (tmp_row[] is register-indexed)
-                    float t = 0.f;
-#pragma unroll
-                    for (int q = 0; q < QB; ++q)
-                        if (pq[e] == q) t = __ldg(tmp_row[q] + pi[e]);
-                    ptmp[e] = t;
-                }
-                // the one chain inside the window, element by element; UP pairs interleaved
-                for (int u = 0; u < chain_len; ++u) {
-                    float hv[UP], pre[UP];
-                    int kk[UP];
-                    bool in[UP];
-#pragma unroll
-                    for (int e = 0; e < UP; ++e) {
-                        kk[e] = 4 * (pw[e] + 32 * u) + pc[e];
-                        in[e] = simple[e] && kk[e] < a.K;
-                        hv[e] = in[e] ? __ldg(a.hiT + (size_t)pi[e] * a.Kp + kk[e]) : 0.f;
-                    }
-#pragma unroll
-                    for (int e = 0; e < UP; ++e) {
-                        pre[e] = in[e] ? __fadd_rn(ptmp[e], sin[(size_t)pq[e] * a.Kp + kk[e]]) : 0.f;
-                        in[e] = in[e] && ford(__fadd_rn(pre[e], hv[e])) >= thr[e];
-                    }
-                    double la[UP];
-#pragma unroll
-                    for (int e = 0; e < UP; ++e) la[e] = in[e] ? __ldg(a.LAd + (size_t)kk[e] * a.K + pi[e]) : 0.0;
-#pragma unroll
-                    for (int e = 0; e < UP; ++e)
-                        if (in[e]) {
-                            const float x = exact_cand(pre[e], la[e]);
-                            if (x > -FLT_MAX) best_take(best[e], x, kk[e]);
-                        }
-                }
-#pragma unroll
-                for (int e = 0; e < UP; ++e) {
-                    if (!ok[e]) continue;
-                    if (listed[e]) {
-                        const int slot = atomicAdd(scount, 1);
-                        if (slot < GROUP_LIST_CAP) {
-                            slist[slot] = pq[e] << 24 | pi[e];
-                            continue;
-                        }
-                        best[e] = scan_serial(pq[e], pi[e], ptmp[e], thr[e]);  // list full
-                    }
-                    emit(pq[e], pi[e], best[e]);
-                }
-            }
-            __syncthreads();
-            // ---- phase C ------------------------------------------------------------------
-            const int nlisted = min(*scount, GROUP_LIST_CAP);
-            for (int e = warp; e < nlisted; e += NWARP) {
-                const int q = slist[e] >> 24, i = slist[e] & 0xffffff;
-                const int thr = ford(srec[(size_t)q * a.Kp + i].top) - WINDOW_STEPS;
-                float tmpv = 0.f;
-#pragma unroll
-                for (int qq = 0; qq < QB; ++qq)
-                    if (qq == q) tmpv = __ldg(tmp_row[qq] + i);
-                const float4 *col4 = reinterpret_cast<const float4 *>(a.hiT + (size_t)i * a.Kp);
-                Best b{-FLT_MAX, 0x7fffffff};
-#pragma unroll 4
-                for (int t = lane; t < Kp4; t += 32) {
-                    const float4 h = __ldg(col4 + t);
-                    const float4 dv = sin4[q * Kp4 + t];
-                    const float hh[4] = {h.x, h.y, h.z, h.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int k = 4 * t + c;
-                        const float pre = __fadd_rn(tmpv, dd[c]);
-                        if (k < a.K && ford(__fadd_rn(pre, hh[c])) >= thr) {
-                            const float x = exact_cand(pre, __ldg(a.LAd + (size_t)k * a.K + i));
-                            if (x > -FLT_MAX) best_take(b, x, k);
-                        }
-                    }
-                }
-                b = warp_best(b);
-                if (lane == 0) emit(q, i, b);
-            }
-            __syncthreads();
-            cur ^= 1;
-        }
-    }
-}
-
 // ---- end of a full-range pass: Ans[T-1] = first argmax of delta (F:188-195, F:251-258) ----
 __global__ void __launch_bounds__(256) k_flash_end(const VecDesc *__restrict__ vecs, int nvec,
                                                    const float *__restrict__ delta, int K, int Kp, int T,
@@ -660,9 +357,8 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
     if (time_it) FV_CUDA(cudaEventRecord(ctx->ev[2], st));
     const float *final_delta = d0;
     const bool persistent = p->engine == FLASHV_ENGINE_PERSISTENT && pass.nvec == 1;
-    // many vectors over a table small enough that two delta sets of 8 vectors fit in shared memory
-    const size_t group_smem = group_smem_bytes(8, Kp);
-    const bool grouped = p->engine != FLASHV_ENGINE_STEP && pass.nvec >= 2 * ctx->sm_count && group_smem <= 200 * 1024;
+    // many vectors over a table small enough that the deltas of a group stay in shared memory (flash_group.cu)
+    const bool grouped = p->engine != FLASHV_ENGINE_STEP && pass.nvec >= 2 * ctx->sm_count && group_engine_fits(m);
     if (!grouped) {  // the group kernel builds its start vectors itself
         dim3 ig((K + 255) / 256, pass.nvec < 65535 ? pass.nvec : 65535);
         k_flash_init<<<ig, 256, 0, st>>>(vecs, pass.nvec, p->d_ob, p->d_ans, T, m->LAd, m->LBd, m->LPi, K, Kp, d0);
@@ -670,27 +366,8 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
         ++p->launches;
     }
     if (grouped) {
-        GroupArgs g;
-        g.hiT = m->hiT, g.LAd = m->LAd, g.LBd = m->LBd, g.LPi = m->LPi, g.LBf = m->LBf, g.K = K, g.Kp = Kp;
-        g.vecs = vecs, g.nvec = pass.nvec, g.ob = p->d_ob, g.ans = p->d_ans, g.T = T;
-        g.dfinal = d1, g.psi = p->d_psi, g.psi16 = p->psi16;
-        const size_t smem = group_smem;
-        const int ngroups = (pass.nvec + 7) / 8;
-        // two 8-warp CTAs per SM when their buffers fit (one resolves while the other streams), else
-        // one 16-warp CTA; either way 128 registers per thread, looping over groups
-        static const int force_warps = getenv("FLASHV_GROUP_WARPS") ? atoi(getenv("FLASHV_GROUP_WARPS")) : 0;
-        const bool two = force_warps ? force_warps == 8 : 2 * (smem + 1024) <= (size_t)ctx->smem_optin;
-        if (two) {
-            FV_CUDA(cudaFuncSetAttribute(k_flash_group_pass<8, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = std::min(2 * ctx->sm_count, ngroups);
-            k_flash_group_pass<8, 2, 8><<<grid, 256, smem, st>>>(g);
-        } else {
-            FV_CUDA(cudaFuncSetAttribute(k_flash_group_pass<8, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = std::min(ctx->sm_count, ngroups);
-            k_flash_group_pass<8, 2, 16><<<grid, 512, smem, st>>>(g);
-        }
-        FV_CUDA(cudaGetLastError());
-        ++p->launches;
+        int rc = group_run_pass(p, pass, d1);
+        if (rc != FLASHV_OK) return rc;
         final_delta = d1;
     } else if (persistent) {
         int rc = persistent_pass(p, pass);

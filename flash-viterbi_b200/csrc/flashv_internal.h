@@ -87,6 +87,7 @@ struct flashv_model {
     int Kp = 0;               // K rounded up to a multiple of 128 (one warp x float4)
     float *hiT = nullptr;     // [K][Kp]  (float)log A, destination-major: hiT[i][k] = log A[k][i]; pad = -inf
     float *hiC = nullptr;     // K*Kp     the same, CTA-tiled for the persistent engine (tile_geom.h)
+    float *hiS = nullptr;     // [Kp][Kp] the same, source-major (hiS[k][i]), for the group engine; only when Kp <= 1536
     int tile_G = 0;           // grid the tiling was built for (min(#SM, K))
     double *LAd = nullptr;    // [K][K]   log A, source-major as the reference stores A (F:27)
     float *LBf = nullptr;     // [M][Kp]  (float)log B, symbol-major: LBf[o][i] — the per-step "tmp" (F:167)
@@ -142,6 +143,9 @@ void build_tiled_slice(const double *LAd, float *hiC, int K, int Kp, int col_beg
 int shard_build_table(flashv_plan *p);
 
 int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it);
+bool group_engine_fits(const flashv_model *m);                       // flash_group.cu
+int group_run_pass(flashv_plan *p, const Pass &pass, float *dfinal);  // flash_group.cu
+constexpr int GROUP_MAX_KP = 1536;  // largest padded K the group engine's shared-memory buffers hold
 int bs_run_pass(flashv_plan *p, const Pass &pass);
 
 int flash_single_step(flashv_model *m, const float *d_in_dev, int o, float *d_out_dev, int32_t *psi_dev, int engine);

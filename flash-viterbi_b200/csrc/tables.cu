@@ -60,6 +60,14 @@ __global__ void k_build_tiled(const double *__restrict__ LAd, float *__restrict_
     hiC[tile_off(ncol, Kp, G, il, k)] = v;
 }
 
+// hiS[k][i] = (float)LAd[k][i], Kp x Kp with -inf padding: the group engine's sweep reads it row by row.
+__global__ void k_build_source_major(const double *__restrict__ LAd, float *__restrict__ hiS, int K, int Kp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (i >= Kp) return;
+    hiS[(size_t)k * Kp + i] = (k < K && i < K) ? __double2float_rn(LAd[(size_t)k * K + i]) : -INFINITY;
+}
+
 void build_tiled_slice(const double *LAd, float *hiC, int K, int Kp, int col_begin, int ncol, int G, cudaStream_t st)
 {
     k_build_tiled<<<dim3((ncol + 255) / 256, Kp), 256, 0, st>>>(LAd, hiC, K, Kp, col_begin, ncol, G);
@@ -128,13 +136,17 @@ int tables_build(flashv_model *m, const float *A, const float *B, const float *P
     TB_CUDA(cudaMalloc(&m->LAd, nA * sizeof(double)));
     TB_CUDA(cudaMalloc(&m->hiT, (size_t)K * Kp * sizeof(float)));
     TB_CUDA(cudaMalloc(&m->hiC, (size_t)K * Kp * sizeof(float)));
+    if (Kp <= GROUP_MAX_KP) {
+        TB_CUDA(cudaMalloc(&m->hiS, (size_t)Kp * Kp * sizeof(float)));
+        m->bytes += (size_t)Kp * Kp * sizeof(float);
+    }
     TB_CUDA(cudaMalloc(&m->LBf, (size_t)M * Kp * sizeof(float)));
     TB_CUDA(cudaMalloc(&m->LBd, (size_t)M * K * sizeof(double)));
     TB_CUDA(cudaMalloc(&m->LPi, (size_t)K * sizeof(double)));
     TB_CUDA(cudaMalloc(&m->scratch_f, (size_t)4 * Kp * sizeof(float)));
     TB_CUDA(cudaMalloc(&m->scratch_i, (size_t)2 * Kp * sizeof(int32_t)));
     TB_CUDA(cudaMalloc(&m->scratch_x, (size_t)2 * Kp * 8));
-    m->bytes = nA * sizeof(double) + (size_t)2 * K * Kp * 4 + (size_t)M * Kp * 4 + (size_t)M * K * 8 + (size_t)K * 8 +
+    m->bytes += nA * sizeof(double) + (size_t)2 * K * Kp * 4 + (size_t)M * Kp * 4 + (size_t)M * K * 8 + (size_t)K * 8 +
                (size_t)6 * Kp * 4;
     TB_CUDA(cudaMemcpyAsync(m->LAd, hLA, nA * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     TB_CUDA(cudaMemcpyAsync(m->LBf, hLBf.data(), hLBf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -144,6 +156,10 @@ int tables_build(flashv_model *m, const float *A, const float *B, const float *P
     dim3 grid((K + 31) / 32, (Kp + 31) / 32), block(32, 8);
     k_transpose_to_f32<<<grid, block, 0, ctx->stream>>>(m->LAd, m->hiT, K, Kp);
     TB_CUDA(cudaGetLastError());
+    if (m->hiS) {
+        k_build_source_major<<<dim3((Kp + 255) / 256, Kp), 256, 0, ctx->stream>>>(m->LAd, m->hiS, K, Kp);
+        TB_CUDA(cudaGetLastError());
+    }
     m->tile_G = ctx->sm_count < K ? ctx->sm_count : K;
     build_tiled_slice(m->LAd, m->hiC, K, Kp, 0, K, m->tile_G, ctx->stream);
     TB_CUDA(cudaGetLastError());

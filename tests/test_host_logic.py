@@ -104,6 +104,67 @@ def test_window_filter_bound():
         assert (fb, fa) == (best, arg)
 
 
+def _sum_first_threshold(top, tmp):
+    """filter_threshold() of flash_group.cu in numpy float32."""
+    c = np.float32(top + tmp)
+    e = (int(np.array([c], np.float32).view(np.int32)[0]) >> 23) & 0xFF
+    G = np.array([max(e - 23, 1) << 23], np.int32).view(np.float32)[0]
+    return np.float32(np.float64(top) - 12.0 * np.float64(G))  # one rounding, like the FFMA
+
+
+def test_sum_first_filter_bound():
+    """The group engine keeps the maximum of m2 = delta[k] + (float)logA[k][i] (two operations per
+    update; the emission term tmp is applied afterwards).  Its window — m2 >= top - 12 G, G the float
+    spacing at |top + tmp| — must contain the reference's first-argmax of
+    (float)((double)(float)(tmp + delta[k]) + logA), also when |tmp| dwarfs |delta + logA|, near
+    powers of two, with ties and with -inf entries (flash_group.cu: filter_threshold)."""
+    rng = np.random.RandomState(23)
+    NEG = np.float32(-3.4028234663852886e38)
+    widest = 0
+    for trial in range(1500):
+        K = 193
+        kind = trial % 5
+        tmp = np.float32(-rng.uniform(0.0, 6))
+        scale = float(rng.choice([1, 40, 400, 4000]))
+        d = (np.float32(-rng.uniform(0, 5, K)) - np.float32(rng.uniform(0, 10) * scale)).astype(np.float32)
+        A = rng.uniform(0.01, 1, K) * (rng.uniform(0, 1, K) < 0.4)
+        A = (A / max(A.sum(), 1e-9)).astype(np.float32)
+        if kind == 1:
+            tmp = np.float32(-rng.uniform(20, 90))  # tmp much larger than delta + logA
+            d = np.float32(-rng.uniform(0, 1.0, K))
+        if kind == 2:  # sums straddling a power of two
+            pw = np.float32(2.0 ** rng.randint(1, 13))
+            d = (-pw - np.float32(rng.uniform(-3, 3, K))).astype(np.float32)
+        if kind == 3:
+            A[rng.randint(0, K, 60)] = A[rng.randint(0, K)]  # repeated values: exact ties
+            d[:] = d[0]
+        if kind == 4:
+            d[rng.randint(0, K, 20)] = NEG  # dead sources
+        with np.errstate(divide="ignore"):
+            la = np.log(A.astype(np.float64))
+        pre = (tmp + d).astype(np.float32)
+        with np.errstate(over="ignore", invalid="ignore"):
+            exact = (pre.astype(np.float64) + la).astype(np.float32)
+            m2 = (d + la.astype(np.float32)).astype(np.float32)
+        best, arg = NEG, -1
+        for k in range(K):
+            if exact[k] > best:
+                best, arg = exact[k], k
+        top = m2.max()
+        if not top > NEG:
+            assert arg == -1
+            continue
+        thr = _sum_first_threshold(top, tmp)
+        cand = np.nonzero(m2 >= thr)[0]
+        widest = max(widest, len(cand))
+        fb, fa = NEG, -1
+        for k in cand:
+            if exact[k] > fb:
+                fb, fa = exact[k], int(k)
+        assert (fb, fa) == (best, arg), (trial, kind)
+    assert widest >= 2  # the ties did produce multi-candidate windows
+
+
 def test_header_declares_only_exported_symbols(fv):
     text = (ROOT / "include" / "flashv.h").read_text()
     declared = sorted(set(re.findall(r"\b(flashv_[a-z_A-Z0-9]+)\s*\(", text)))
