@@ -197,7 +197,8 @@ extern "C" int flashv_plan_create(flashv_model *m, int T, int N, int batch, int 
     }
     if (engine == FLASHV_ENGINE_AUTO) engine = ctx->coop ? FLASHV_ENGINE_PERSISTENT : FLASHV_ENGINE_STEP;
     p->engine = engine;
-    p->psi16 = m->K < 65535 ? 1 : 0;
+    // FLASH-BS keeps one flag bit in every backpointer entry (bs_kernels.cu)
+    p->psi16 = (B > 0 ? m->K < 32768 : m->K < 65535) ? 1 : 0;
 
     std::vector<VecDesc> all;
     if (p->sched.first_pass) {
@@ -238,6 +239,8 @@ extern "C" int flashv_plan_create(flashv_model *m, int T, int N, int batch, int 
     PL_ALLOC(p->d_sync, 256);
     if (B == 0) {
         PL_ALLOC(p->d_delta, delta_bytes);
+    } else {
+        PL_ALLOC(p->d_bs_score, (size_t)max_rows * K * sizeof(float));  // score vectors for backtrack-time repairs
     }
 #undef PL_ALLOC
     if (rc == FLASHV_OK && p->d_delta && (e = cudaMemsetAsync(p->d_delta, 0, delta_bytes, ctx->stream)) != cudaSuccess)

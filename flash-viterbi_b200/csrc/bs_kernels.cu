@@ -20,24 +20,60 @@
 
 namespace flashv {
 
-// Floyd sift of S:96-123 for one node; hv/hs are 0-based images of heap slots 1..total.
-__device__ __forceinline__ void heap_sift_held(float *hv, int *hs, int total, int parent, float v, int st)
+// A heap entry as the kernels keep it: slot n (1-based, like the reference's array) lives at
+// node[n] = {Value bits, State}; the two children of n are the 16 bytes at node[2n], so a sift level
+// is one 128-bit shared-memory load.  node[B+1] is a sentinel with Value = +inf (never the smaller
+// child), node[0] is unused.
+struct __align__(8) HeapNode {
+    float v;
+    int s;
+};
+
+// Sift of S:96-123 / S:141-163 from `parent` with the held entry (v, st): follow the smaller child
+// (the right one only if strictly smaller, S:146), stop at the first child that is >= v (S:152: ties
+// stop the sift).
+__device__ __forceinline__ void heap_sift_held(HeapNode *node, int total, int parent, float v, int st)
 {
     int child = 2 * parent;
     while (child <= total) {
-        float cv = hv[child - 1];
-        if (child + 1 <= total) {
-            float rv = hv[child];
-            if (cv > rv) ++child, cv = rv;
-        }
-        if (v <= cv) break;  // S:114 / S:152: ties stop the sift
-        hv[parent - 1] = cv;
-        hs[parent - 1] = hs[child - 1];
+        const uint4 pair = *reinterpret_cast<const uint4 *>(node + child);
+        float cv = __uint_as_float(pair.x);
+        int cs = (int)pair.y;
+        const float rv = __uint_as_float(pair.z);
+        if (cv > rv) ++child, cv = rv, cs = (int)pair.w;
+        if (v <= cv) break;
+        node[parent] = HeapNode{cv, cs};
         parent = child;
         child *= 2;
     }
-    hv[parent - 1] = v;
-    hs[parent - 1] = st;
+    node[parent] = HeapNode{v, st};
+}
+
+// The same sift from the root for the streaming part, where one lane runs it hundreds of times per
+// step and its latency is the step's critical path.  The four grandchildren of the current node
+// (32 contiguous bytes at node[4n]) are fetched while the children are being compared, so a level
+// costs a short ALU chain instead of a shared-memory round trip.  Reads run ahead of the heap's
+// end (up to node[2*total+3]): the buffer is that long, and entries past total+1 are never used.
+__device__ __forceinline__ void heap_replace_root(HeapNode *node, int total, float v, int st)
+{
+    int n = 1;
+    if (total >= 2) {
+        uint4 kids = *reinterpret_cast<const uint4 *>(node + 2);
+        uint4 ga = *reinterpret_cast<const uint4 *>(node + 4), gb = *reinterpret_cast<const uint4 *>(node + 6);
+        while (true) {
+            const bool right = __uint_as_float(kids.x) > __uint_as_float(kids.z);
+            const float cv = __uint_as_float(right ? kids.z : kids.x);
+            const int cs = (int)(right ? kids.w : kids.y);
+            if (v <= cv) break;
+            node[n] = HeapNode{cv, cs};
+            n = 2 * n + (right ? 1 : 0);
+            if (2 * n > total) break;
+            kids = right ? gb : ga;
+            ga = *reinterpret_cast<const uint4 *>(node + 4 * n);
+            gb = *reinterpret_cast<const uint4 *>(node + 4 * n + 2);
+        }
+    }
+    node[n] = HeapNode{v, st};
 }
 
 // Replay of generate_state_heap() (S:167-211) over score[0..K-1] by one warp.
@@ -46,11 +82,28 @@ __device__ __forceinline__ void heap_sift_held(float *hv, int *hs, int total, in
 //   i >= B     : if score_i > H[1].Value replace root + sift     S:193-203
 // Nodes of one depth have disjoint subtrees, so Floyd's node = total/2..1 order is reproduced by
 // doing depths deepest-first with the nodes of a depth spread over lanes.  The streaming part
-// ballots 32 scores at a time against the current minimum (which only grows), so lanes only
-// serialise on entries that can still enter.
-__device__ void heap_replay_warp(const float *score, int K, int B, float *hv, int *hs, int lane)
+// ballots 32 scores at a time against the current minimum (which only grows); lane 0 then sifts the
+// survivors one after the other — a sift is a chain of dependent 16-byte shared-memory loads, about
+// 50 cycles per level, and nothing in it can be shared between lanes.
+// With WAIT the scores arrive while the replay runs: chunk c (states 32c..32c+31) is complete once
+// tags[c] == tag (written by the scoring warps of the same CTA).
+template <bool WAIT>
+__device__ void heap_replay_warp(const float *score, int K, int B, HeapNode *node, int lane, const volatile int *tags,
+                                 int tag)
 {
-    for (int s = lane; s < B; s += 32) hv[s] = score[s], hs[s] = s;
+    auto wait_upto = [&](int last_state) {  // scores [0, last_state] are final
+        if (!WAIT) return;
+        const int c1 = min(last_state, K - 1) >> 5;
+        while (tags[c1] != tag) {
+        }
+        // chunks complete in any order: the earlier ones were awaited by earlier calls, except
+        // for the first call (the initial B states)
+        __threadfence_block();
+    };
+    if (WAIT)
+        for (int c = 0; c <= ((B - 1) >> 5); ++c) wait_upto(32 * c);
+    for (int s = lane; s < B; s += 32) node[s + 1] = HeapNode{score[s], s};
+    if (lane == 0) node[B + 1] = HeapNode{INFINITY, -1};
     __syncwarp();
     const int last_parent = B / 2;
     if (last_parent >= 1) {
@@ -58,91 +111,33 @@ __device__ void heap_replay_warp(const float *score, int K, int B, float *hv, in
         for (; depth >= 0; --depth) {
             const int lo = 1 << depth;
             const int hi = min((2 << depth) - 1, last_parent);
-            for (int node = lo + lane; node <= hi; node += 32) heap_sift_held(hv, hs, B, node, hv[node - 1], hs[node - 1]);
+            for (int n = lo + lane; n <= hi; n += 32) {
+                const HeapNode held = node[n];
+                heap_sift_held(node, B, n, held.v, held.s);
+            }
             __syncwarp();
         }
     }
-    float mn = hv[0];
-    if (B >= 2 && B <= 128) {
-        // Streaming part for beams of up to 128 entries.  Which child a sift follows depends only on
-        // the heap, not on the new value, so every lane keeps, per depth d, a bit mask "the right
-        // child of the j-th node of depth d is strictly smaller" (S:146).  The root-to-leaf min-child
-        // path is then a handful of ALU operations that every lane computes redundantly, so no
-        // shuffle is needed to agree on it: lane d fetches the entry at depth d, one ballot finds
-        // where the new value stops (S:152: first depth with v <= entry), lanes shift the entries
-        // above it up by one depth, and a second ballot refreshes the bits of the nodes whose
-        // children changed.  Three shared-memory round trips per replacement, none per depth.
-        constexpr int MAXD = 7;  // depth of node 128
-        unsigned long long dm[MAXD];  // dm[d] bit j: node 2^d + j prefers its right child (depths 0..6)
-#pragma unroll
-        for (int d = 0; d < MAXD; ++d) {
-            dm[d] = 0;
-            const int first = 1 << d, count = 1 << d;
-            for (int base = 0; base < count; base += 32) {
-                const int n = first + base + lane;
-                const bool r = base + lane < count && 2 * n + 1 <= B && hv[2 * n - 1] > hv[2 * n];
-                dm[d] |= (unsigned long long)__ballot_sync(FULL_MASK, r) << base;
-            }
-        }
-        for (int base = B; base < K; base += 32) {
-            const int i = base + lane;
-            const float s = i < K ? score[i] : -INFINITY;
-            unsigned enter = __ballot_sync(FULL_MASK, s > mn);
-            while (enter) {
-                const int l0 = __ffs(enter) - 1;
-                enter &= enter - 1;
-                const float v = score[base + l0];
-                if (!(v > mn)) continue;  // S:193, against the minimum as it is now
-                // min-child path: jd[d] = index within depth d of the path node, depth = last depth
-                int jd[MAXD + 1];
-                int depth = 0;
-                jd[0] = 0;
-#pragma unroll
-                for (int d = 0; d < MAXD; ++d) {
-                    const int node = (1 << d) + jd[d];
-                    const bool more = depth == d && 2 * node <= B;
-                    jd[d + 1] = 2 * jd[d] + (int)((dm[d] >> jd[d]) & 1ull);
-                    if (more) depth = d + 1;
-                }
-                int mine = 1, parent = 1;  // path node at this lane's depth and the one above it
-#pragma unroll
-                for (int d = 1; d <= MAXD; ++d)
-                    if (lane == d) mine = (1 << d) + jd[d], parent = (1 << (d - 1)) + jd[d - 1];
-                const bool on_path = lane >= 1 && lane <= depth;
-                const float cv = on_path ? hv[mine - 1] : 0.f;
-                const int cs = on_path ? hs[mine - 1] : 0;
-                const unsigned stopm = __ballot_sync(FULL_MASK, on_path && v <= cv);
-                const int stop = stopm ? __ffs(stopm) - 1 : depth + 1;  // v ends at depth stop-1
-                if (on_path && lane < stop) hv[parent - 1] = cv, hs[parent - 1] = cs;
-                if (lane == stop - 1) hv[mine - 1] = v, hs[mine - 1] = base + l0;  // lane 0 has mine == 1
-                __syncwarp();
-                // nodes at depths 0 .. stop-2 had a child replaced: refresh their bits
-                const bool upd = lane + 1 < stop && 2 * mine + 1 <= B;
-                const bool nb = upd && hv[2 * mine - 1] > hv[2 * mine];
-                const unsigned updm = __ballot_sync(FULL_MASK, upd), setm = __ballot_sync(FULL_MASK, nb);
-#pragma unroll
-                for (int d = 0; d < MAXD; ++d)
-                    if (updm >> d & 1u) dm[d] = (dm[d] & ~(1ull << jd[d])) | ((unsigned long long)(setm >> d & 1u) << jd[d]);
-                // the new minimum: the value itself if it stayed at the root, else the old depth-1 entry
-                mn = stop == 1 ? v : __shfl_sync(FULL_MASK, cv, 1);
-            }
-        }
-        __syncwarp();
-        return;
-    }
+    float mn = node[1].v;
     for (int base = B; base < K; base += 32) {
+        wait_upto(base + 31);
+        if (WAIT && ((base + 31) >> 5) != (base >> 5)) wait_upto(base);  // B not a multiple of 32: two chunks
         const int i = base + lane;
         const float s = i < K ? score[i] : -INFINITY;
         unsigned enter = __ballot_sync(FULL_MASK, s > mn);
-        while (enter) {
-            const int l = __ffs(enter) - 1;
-            enter &= enter - 1;
-            const float sv = __shfl_sync(FULL_MASK, s, l);
-            if (sv > mn) {  // S:193, against the minimum as it is now
-                if (lane == 0) heap_sift_held(hv, hs, B, 1, sv, base + l);
-                __syncwarp();
-                mn = hv[0];
+        if (enter) {
+            if (lane == 0) {
+                while (enter) {
+                    const int l = __ffs(enter) - 1;
+                    enter &= enter - 1;
+                    const float v = score[base + l];
+                    if (v > mn) {  // S:193, against the minimum as it is now
+                        heap_replace_root(node, B, v, base + l);
+                        mn = node[1].v;
+                    }
+                }
             }
+            mn = __shfl_sync(FULL_MASK, mn, 0);
         }
     }
     __syncwarp();
@@ -159,24 +154,145 @@ struct BsArgs {
     float *score;
     void *psi;
     int psi16;
+    int flagbit;        // backpointer-entry bit "several beam states attain this maximum"
+    float *rows;        // [psi rows][K] score vectors of the steps mid .. R-1 (row of step j-1 = backpointer row of step j)
+    int always_replay;  // FLASHV_BS_REPLAY=1: rebuild the heap by replay at every step (the slow, literal path)
     const uint8_t *ismid;
-    long long *trace;  // optional: per CTA {score cycles, heap cycles} (FLASHV_BS_TRACE), else null
+    long long *trace;  // optional: per CTA {score cycles, beam cycles} (FLASHV_BS_TRACE), else null
 };
 
-// dynamic shared memory: float sscore[Kp]; float hv[2][B]; int hs[2][B]
+// ---- the beam of one step ---------------------------------------------------------------------
+// What the NEXT step needs from the reference's heap is, almost always, only the SET of its B
+// entries: a destination's value max_c x_c does not depend on the slot order, and its argmax does
+// only when two beam states attain the maximum exactly (S:440-446 then keeps the first slot).
+// The set is "the B largest scores": an entry above the final minimum tau can never have been
+// evicted or refused (the root only grows), so the heap holds every score > tau plus some == tau;
+// if the scores == tau are exactly as many as the free slots, the set is decided without knowing
+// the heap's layout.  So per step the CTA runs a radix select (4 passes of 8 bits over a monotone
+// integer key) instead of replaying K sequential heap insertions, and falls back to the replay
+//   * when several scores tie at tau (the heap's layout decides which of them stay),
+//   * at the last step of a full-range pass (the end scan S:376-381 reads slot positions),
+//   * at backtrack time for a visited backpointer whose maximum was attained twice: the score
+//     vector of the step before is kept in HBM, its heap is replayed and the destination is
+//     re-evaluated in true slot order (bs_fix_entry).
+// Nothing is approximated: the fast path is taken only where it provably equals the replay.
+struct BeamScratch {
+    int hist[256];
+    unsigned prefix;
+    int need, count, ambiguous;
+};
+
+__device__ __forceinline__ unsigned score_key(float x)  // monotone: larger score <=> larger key
+{
+    return (unsigned)ford(x) ^ 0x80000000u;
+}
+
+// Whole CTA.  On return beam[0..B-1] holds the heap's entries (any order, or slots 1..B after a
+// replay) and the return value says whether the replay ran (node[1..B] is then the true heap).
+__device__ bool build_beam(const float *sscore, int K, int B, HeapNode *beam, HeapNode *node, BeamScratch *bs, bool force_replay)
+{
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    bool replay = force_replay;
+    if (!replay) {
+        if (tid == 0) bs->prefix = 0, bs->need = B, bs->count = 0, bs->ambiguous = 0;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (int b = tid; b < 256; b += nthr) bs->hist[b] = 0;
+            __syncthreads();
+            const unsigned prefix = bs->prefix;
+            const unsigned himask = pass == 0 ? 0u : 0xffffffffu << (shift + 8);
+            for (int i = tid; i < K; i += nthr) {
+                const unsigned u = score_key(sscore[i]);
+                if ((u & himask) == prefix) atomicAdd(&bs->hist[(u >> shift) & 255], 1);
+            }
+            __syncthreads();
+            if (tid < 32) {
+                // bins from the top: the bin holding the need-th largest key
+                int need = bs->need, found = -1, above = 0;
+                for (int hi = 255; hi >= 0 && found < 0; hi -= 32) {
+                    const int b = hi - tid;  // lane 0 owns the highest bin of this group
+                    const int c = bs->hist[b];
+                    int incl = c;  // inclusive prefix over lanes 0..tid (bins hi .. b)
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int t = __shfl_up_sync(FULL_MASK, incl, off);
+                        if (tid >= off) incl += t;
+                    }
+                    const unsigned hit = __ballot_sync(FULL_MASK, above + incl >= need);
+                    if (hit) {
+                        const int l = __ffs(hit) - 1;
+                        found = hi - l;
+                        const int before = __shfl_sync(FULL_MASK, incl - c, l);  // keys in higher bins of this group
+                        need -= above + before;
+                    } else {
+                        above += __shfl_sync(FULL_MASK, incl, 31);
+                    }
+                }
+                if (tid == 0) {
+                    bs->prefix = prefix | (unsigned)found << shift;
+                    bs->need = need;
+                    if (pass == 3) bs->ambiguous = bs->hist[found] != need;  // several scores == tau and not all fit
+                }
+            }
+            __syncthreads();
+        }
+        replay = bs->ambiguous != 0;
+        if (!replay) {
+            const unsigned tau = bs->prefix;
+            for (int i = tid; i < K; i += nthr) {
+                const float x = sscore[i];
+                if (score_key(x) >= tau) beam[atomicAdd(&bs->count, 1)] = HeapNode{x, i};
+            }
+        }
+    }
+    if (replay) {
+        if (tid < 32) heap_replay_warp<false>(sscore, K, B, node, tid, nullptr, 0);
+        __syncthreads();
+        for (int c = tid; c < B; c += nthr) beam[c] = node[c + 1];
+    }
+    __syncthreads();
+    return replay;
+}
+
+// Exact backpointer of destination state i at a step whose previous score vector is `row`
+// (executed by warp 0): replay the heap, then S:440-446 in slot order.
+__device__ int bs_fix_entry(const BsArgs &a, const float *row, int i, int o, HeapNode *node, int lane)
+{
+    heap_replay_warp<false>(row, a.K, a.B, node, lane, nullptr, 0);
+    const float tmp = __ldg(a.LBf + (size_t)o * a.Kp + i);
+    Best b{-FLT_MAX, 0x7fffffff};
+    for (int c = 1 + lane; c <= a.B; c += 32) {
+        const HeapNode h = node[c];
+        const float x = exact_cand(__fadd_rn(tmp, h.v), __ldg(a.LAd + (size_t)h.s * a.K + i));
+        if (x > -FLT_MAX) best_take(b, x, c);  // larger value, then the earlier slot
+    }
+    b = warp_best(b);
+    return b.k == 0x7fffffff ? -1 : node[b.k].s;
+}
+
+// dynamic shared memory: float sscore[Kp]; HeapNode beam[B] ; HeapNode node[2B+4]; BeamScratch
 __global__ void __launch_bounds__(1024) k_bs_pass(const BsArgs a)
 {
-    extern __shared__ float smem_f[];
+    extern __shared__ float4 smem_f4[];
+    float *smem_f = reinterpret_cast<float *>(smem_f4);
     const int K = a.K, B = a.B, T = a.T;
     float *sscore = smem_f;
-    float *hv0 = smem_f + a.Kp;
-    int *hs0 = reinterpret_cast<int *>(hv0 + 2 * B);
+    HeapNode *beam = reinterpret_cast<HeapNode *>(smem_f + a.Kp);
+    HeapNode *node = beam + ((B + 1) & ~1);
+    BeamScratch *bs = reinterpret_cast<BeamScratch *>(node + 2 * B + 4);
+    __shared__ int s_state;
     const int v = blockIdx.x;
     if (v >= a.nvec) return;
     const VecDesc vd = a.vecs[v];
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const int32_t *ob = a.ob + (size_t)vd.seq * T;
     int32_t *ans = a.ans + (size_t)vd.seq * T;
+    const bool full = (vd.flags & VEC_FULL_RANGE) != 0;
+    auto keep_row = [&](int j) {  // the scores of step j are the "previous scores" of backpointer row j+1
+        if (j < vd.mid || j > vd.R - 1) return;
+        float *dst = a.rows + (size_t)(vd.psi_row + (j - vd.mid)) * K;
+        for (int i = tid; i < K; i += nthr) dst[i] = sscore[i];
+    };
 
     // start vector, S:411-426 (S:314-320 for the first pass).  prev < 0 is the reference's
     // vit->A[-1][i], which aliases Pi[i].
@@ -189,81 +305,98 @@ __global__ void __launch_bounds__(1024) k_bs_pass(const BsArgs a)
         }
     }
     __syncthreads();
-    int cur = 0;
-    if (warp == 0) heap_replay_warp(sscore, K, B, hv0, hs0, lane);
-    __syncthreads();
+    keep_row(vd.L);
+    bool have_heap = build_beam(sscore, K, B, beam, node, bs, a.always_replay || (full && vd.R == vd.L));
 
-    long long t_score = 0, t_heap = 0;
+    long long t_score = 0, t_beam = 0;
     for (int j = vd.L + 1; j <= vd.R; ++j) {
         const long long c0 = clock64();
-        const float *hv = hv0 + cur * B;
-        const int *hs = hs0 + cur * B;
         const int o = ob[j];
         const bool keep = j >= vd.mid + 1;  // S:448: payload latches at j == mid+1
         for (int i = tid; i < K; i += nthr) {
             const float tmp = __ldg(a.LBf + (size_t)o * a.Kp + i);  // S:439
             float best = -FLT_MAX;
             int arg = -1;
-            // S:440-446, slots in array order, strict '>'.  The row reads are independent of the
-            // running maximum: fetch a batch of them before the compare chain consumes any.
+            bool tie = false;
+            // S:440-446 over the beam.  The row reads are independent of the running maximum: fetch
+            // a batch of them before the compare chain consumes any.
             constexpr int UB = 8;
-            int c = 0;
-            for (; c + UB <= B; c += UB) {
+            int e0 = 0;
+            for (; e0 + UB <= B; e0 += UB) {
                 double la[UB];
 #pragma unroll
-                for (int e = 0; e < UB; ++e) la[e] = __ldg(a.LAd + (size_t)hs[c + e] * K + i);
+                for (int e = 0; e < UB; ++e) la[e] = __ldg(a.LAd + (size_t)beam[e0 + e].s * K + i);
 #pragma unroll
                 for (int e = 0; e < UB; ++e) {
-                    const float x = exact_cand(__fadd_rn(tmp, hv[c + e]), la[e]);
-                    if (x > best) best = x, arg = c + e;
+                    const HeapNode h = beam[e0 + e];
+                    const float x = exact_cand(__fadd_rn(tmp, h.v), la[e]);
+                    tie = x > best ? false : (tie || (x == best && arg >= 0));
+                    if (x > best) best = x, arg = h.s;
                 }
             }
-            for (; c < B; ++c) {
-                const float x = exact_cand(__fadd_rn(tmp, hv[c]), __ldg(a.LAd + (size_t)hs[c] * K + i));
-                if (x > best) best = x, arg = c;
+            for (; e0 < B; ++e0) {
+                const HeapNode h = beam[e0];
+                const float x = exact_cand(__fadd_rn(tmp, h.v), __ldg(a.LAd + (size_t)h.s * K + i));
+                tie = x > best ? false : (tie || (x == best && arg >= 0));
+                if (x > best) best = x, arg = h.s;
             }
             sscore[i] = best;
-            if (keep) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + i, arg < 0 ? -1 : hs[arg]);
+            // with the true heap in beam[] (slot order) the first maximum IS the reference's choice
+            if (keep) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + i,
+                                arg >= 0 && tie && !have_heap ? arg | a.flagbit : arg);
         }
         __syncthreads();
         const long long c1 = clock64();
-        if (warp == 0) heap_replay_warp(sscore, K, B, hv0 + (cur ^ 1) * B, hs0 + (cur ^ 1) * B, lane);
-        __syncthreads();
-        t_score += c1 - c0, t_heap += clock64() - c1;
-        cur ^= 1;
+        keep_row(j);
+        have_heap = build_beam(sscore, K, B, beam, node, bs, a.always_replay || (full && j == vd.R));
+        t_score += c1 - c0, t_beam += clock64() - c1;
     }
-    if (a.trace && tid == 0) a.trace[2 * v] = t_score, a.trace[2 * v + 1] = t_heap;
+    if (a.trace && tid == 0) a.trace[2 * v] = t_score, a.trace[2 * v + 1] = t_beam;
 
+    // ---- end state: S:374-383 / S:454-463 for a full-range pass, Find_T3_State (S:73-86) otherwise ----
     if (tid == 0) {
-        const float *hv = hv0 + cur * B;
-        const int *hs = hs0 + cur * B;
-        int state;
-        if (vd.flags & VEC_FULL_RANGE) {  // S:374-383 / S:454-463
-            float sc = hv[0];
-            int arg = 0;
-            for (int c = B / 2 + 1; c < B; ++c)
-                if (hv[c] > sc) arg = c, sc = hv[c];
-            state = hs[arg];
+        int state = -1;
+        if (full) {  // have_heap: slot 1, then slots B/2+2 .. B of the true heap
+            float sc = node[1].v;
+            int arg = 1;
+            for (int c = B / 2 + 2; c <= B; ++c)
+                if (node[c].v > sc) arg = c, sc = node[c].v;
+            state = node[arg].s;
             ans[vd.R] = state;
             a.score[vd.seq] = sc;
-        } else {  // Find_T3_State, S:73-86: -1 when Ans[R] fell out of the beam
+        } else {  // -1 when Ans[R] fell out of the beam
             const int want = ans[vd.R];
-            state = -1;
             for (int c = 0; c < B; ++c)
-                if (hs[c] == want) {
+                if (beam[c].s == want) {
                     state = want;
                     break;
                 }
         }
+        s_state = state;
+    }
+    __syncthreads();
+    // ---- walk back (warp 0, every lane holds the same state) ------------------------------------------
+    if (tid < 32) {
+        int state = s_state;
         for (int j = vd.R; j >= vd.mid + 1; --j) {
-            if (state >= 0) state = psi_load(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + state);
-            if ((vd.flags & VEC_FIRST_PASS) && a.ismid[j - 1]) ans[j - 1] = state;
+            if (state >= 0) {
+                const size_t ridx = (size_t)(vd.psi_row + (j - vd.mid - 1));
+                const int raw = psi_load(a.psi, a.psi16, ridx * K + state);
+                if (raw >= 0 && (raw & a.flagbit))
+                    state = bs_fix_entry(a, a.rows + ridx * K, state, ob[j], node, lane);
+                else
+                    state = raw;
+            }
+            if (lane == 0 && (vd.flags & VEC_FIRST_PASS) && a.ismid[j - 1]) ans[j - 1] = state;
         }
-        if (!(vd.flags & VEC_FIRST_PASS)) ans[vd.mid] = state;
+        if (lane == 0 && !(vd.flags & VEC_FIRST_PASS)) ans[vd.mid] = state;
     }
 }
 
-static size_t bs_smem_bytes(int Kp, int B) { return (size_t)Kp * 4 + (size_t)B * 16; }
+static size_t bs_smem_bytes(int Kp, int B)
+{
+    return (size_t)Kp * 4 + (size_t)(((B + 1) & ~1) + 2 * B + 4) * sizeof(HeapNode) + sizeof(BeamScratch) + 16;
+}
 
 int bs_run_pass(flashv_plan *p, const Pass &pass)
 {
@@ -275,6 +408,8 @@ int bs_run_pass(flashv_plan *p, const Pass &pass)
     a.vecs = p->d_vecs + pass.vec_offset, a.nvec = pass.nvec;
     a.ob = p->d_ob, a.ans = p->d_ans, a.score = p->d_score;
     a.psi = p->d_psi, a.psi16 = p->psi16, a.ismid = p->d_ismid;
+    a.flagbit = p->psi16 ? 0x8000 : 0x40000000, a.rows = p->d_bs_score;
+    a.always_replay = getenv("FLASHV_BS_REPLAY") ? atoi(getenv("FLASHV_BS_REPLAY")) : 0;  // read per call: tests toggle it
     a.trace = nullptr;
     static long long *d_trace = nullptr;
     const bool tracing = getenv("FLASHV_BS_TRACE") != nullptr;
@@ -296,7 +431,7 @@ int bs_run_pass(flashv_plan *p, const Pass &pass)
         long long h[2];
         FV_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         FV_CUDA(cudaStreamSynchronize(ctx->stream));
-        fprintf(stderr, "[flashv bs trace] nvec=%d steps=%d vector 0: score %lld cycles, heap %lld cycles\n", pass.nvec,
+        fprintf(stderr, "[flashv bs trace] nvec=%d steps=%d vector 0: score %lld cycles, beam %lld cycles\n", pass.nvec,
                 pass.max_steps, h[0], h[1]);
     }
     return FLASHV_OK;
@@ -324,13 +459,12 @@ __global__ void __launch_bounds__(256) k_bs_score_once(const double *__restrict_
 
 __global__ void k_bs_replay_once(const float *__restrict__ score, int K, int B, float *hv_out, int32_t *hs_out, int debug)
 {
-    extern __shared__ float smem_f[];
-    float *hv = smem_f;
-    int *hs = reinterpret_cast<int *>(smem_f + B);
+    extern __shared__ float4 smem_f4[];
+    HeapNode *node = reinterpret_cast<HeapNode *>(smem_f4);
     const long long c0 = clock64();
-    heap_replay_warp(score, K, B, hv, hs, threadIdx.x);
+    heap_replay_warp<false>(score, K, B, node, threadIdx.x, nullptr, 0);
     if (debug && threadIdx.x == 0) printf("[flashv] heap replay K=%d B=%d: %lld cycles (scores in global memory)\n", K, B, clock64() - c0);
-    for (int s = threadIdx.x; s < B; s += 32) hv_out[s] = hv[s], hs_out[s] = hs[s];
+    for (int s = threadIdx.x; s < B; s += 32) hv_out[s] = node[s + 1].v, hs_out[s] = node[s + 1].s;
 }
 
 int bs_single_score(flashv_model *m, const float *hv_dev, const int32_t *hs_dev, int B, int o, float *score_dev,
@@ -344,7 +478,7 @@ int bs_single_score(flashv_model *m, const float *hv_dev, const int32_t *hs_dev,
 
 int bs_single_replay(flashv_ctx *ctx, const float *score_dev, int K, int B, float *hv_dev, int32_t *hs_dev)
 {
-    const size_t smem = (size_t)B * 8;
+    const size_t smem = (size_t)(2 * B + 4) * sizeof(HeapNode);
     FV_CUDA(cudaFuncSetAttribute(k_bs_replay_once, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_bs_replay_once<<<1, 32, smem, ctx->stream>>>(score_dev, K, B, hv_dev, hs_dev, getenv("FLASHV_BS_TRACE") != nullptr);
     FV_CUDA(cudaGetLastError());

@@ -161,6 +161,33 @@ def test_bs_pieces_bit_exact(fv, oracle_mod, gpu_ctx):
     model.close()
 
 
+def test_flash_bs_select_path_equals_replay_path(fv, oracle_mod, gpu_ctx, monkeypatch):
+    """FLASH-BS builds each step's beam with a radix select and replays the reference's heap only
+    where its layout matters (ties at the beam's minimum, the end scan, visited backpointers whose
+    maximum is attained twice).  Both that path and the literal replay-every-step path
+    (FLASHV_BS_REPLAY=1) must give the oracle's path — on a model with many exactly equal scores
+    (quantised probabilities) and on an ordinary one."""
+    rng = np.random.RandomState(97)
+    for K, M, T, quant in [(96, 4, 40, True), (300, 20, 64, False)]:
+        A, B, Pi = random_hmm(K, M, 0.3, 97 + K)
+        if quant:  # a handful of distinct probabilities: exact ties in scores and in candidates
+            A = (np.ceil(A * 8) / 8 * (A > 0)).astype(np.float32)
+            A = (A / np.maximum(A.sum(axis=1, keepdims=True), 1e-9)).astype(np.float32)
+            B = np.full_like(B, 1.0 / M)
+        om = oracle_mod.OracleModel(A, B, Pi)
+        model = fv.Model(gpu_ctx, A, B, Pi)
+        for N, Bw in [(1, 8), (4, 16), (5, 3), (1, K)]:
+            ob = rng.randint(0, M, T).astype(np.int32)
+            want, wscore, _ = om.flash_bs(ob, N, Bw)
+            for mode in ("0", "1"):
+                monkeypatch.setenv("FLASHV_BS_REPLAY", mode)
+                got, score, _ = model.bs_decode(ob, N, Bw)
+                assert np.array_equal(got, want), (K, N, Bw, mode)
+                assert _bits(score) == _bits(wscore), (K, N, Bw, mode)
+        monkeypatch.delenv("FLASHV_BS_REPLAY")
+        model.close()
+
+
 def test_batch_equals_single(fv, oracle_mod, gpu_ctx):
     K, M, T = 200, 12, 48
     A, B, Pi = random_hmm(K, M, 0.15, 41)
