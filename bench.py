@@ -186,6 +186,94 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# side measurements: BASELINE configs 3 and 4 (reported beside the headline line, never as `value`)
+# ------------------------------------------------------------------------------------------------
+def sequential_steps(fv, T, N):
+    """Trellis steps on the critical path of one decode: the N-way pass plus the longest task of every
+    level of the task tree (tasks of a level run side by side on the device)."""
+    tasks, first_pass, mids = fv.task_list(T, N)
+    if first_pass:
+        bounds = [0] + [m + 1 for m in mids]
+        level = [(lo, hi) for lo, hi in zip(bounds, list(mids) + [T - 1])]
+    else:
+        level = [(0, T - 1)]
+    total = T - 1 if first_pass else 0
+    while level:
+        total += max(r - l for l, r in level)
+        nxt = []
+        for l, r in level:
+            if r <= l + 1:
+                continue
+            mid = (l + r) >> 1
+            nxt.append((l, mid))
+            if r > mid + 1:
+                nxt.append((mid + 1, r))
+        level = nxt
+    return total
+
+
+def other_configs(fv, ctx, model, ob, stream, torch):
+    import gen_hmm
+
+    out = {}
+
+    def timed(plan, runs):
+        plan.run()
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(runs):
+                plan.run()
+            e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / runs
+
+    # config 3: FLASH-BS, same model and sequence, beam 128 (latency-bound: report ms and us per sequential step)
+    try:
+        for n_seg in (8, 127):
+            p3 = fv.Plan(model, T, n_seg, 1, 128, fv.ENGINE_AUTO)
+            p3.upload(ob[None, :])
+            ms = timed(p3, 3)
+            seq_steps = sequential_steps(fv, T, n_seg)
+            out[f"flash_bs_B128_N{n_seg}"] = {"workload": f"FLASH-BS K={K} T={T} B=128 N={n_seg}, single sequence", "ms_per_decode": ms,
+                                              "sequential_steps": seq_steps, "us_per_sequential_step": ms * 1e3 / seq_steps,
+                                              "bound": "latency (K x B dependent double reads + beam selection per step)"}
+            p3.close()
+    except Exception as e:
+        out["flash_bs_B128"] = f"failed: {e}"
+
+    # config 4 shape: batched FLASH, K=512, T=1024, N=32; 2368 sequences = one full wave of the group
+    # engine (2 CTAs x 148 SMs x 8 sequences) instead of the config's 8192, to keep the run short
+    try:
+        K4, T4, N4, B4 = 512, 1024, 32, 2368
+        A4, Bm4, Pi4 = gen_hmm.make_hmm(K4, M, 0.253, SEED)
+        f = gen_hmm.as_reference_floats
+        m4 = fv.Model(ctx, f(A4), f(Bm4), f(Pi4))
+        obs4 = np.stack([gen_hmm.observations(T4, M, 1000 + b) for b in range(B4)])
+        p4 = fv.Plan(m4, T4, N4, B4, 0, fv.ENGINE_AUTO)
+        p4.upload(obs4)
+        ms = timed(p4, 2)
+        rep4 = p4.report()
+        S4 = rep4.executed_steps
+        clk_hz = 1.965e9
+        fp32_peak = 148 * 128 * clk_hz  # lane-operations per second
+        executed = S4 * float(K4) * K4 * B4
+        out["batched_K512_T1024"] = {
+            "workload": f"batched FLASH K={K4} T={T4} N={N4}, {B4} sequences on one GPU (config 4 at {B4}/8192 of its batch)",
+            "ms_per_batch": ms, "value": B4 * float(K4) * K4 * T4 / (ms * 1e-3) / 1e9, "unit": UNIT,
+            "executed_steps_per_sequence": S4, "first_pass_ms": rep4.first_pass_ms,
+            "roofline": {"bound": "fp32 pipe (SURVEY 8d: 3 lane-operations per executed update)", "achieved": executed * 3 / (ms * 1e-3) / 1e12,
+                         "peak": fp32_peak / 1e12, "unit": "T lane-op/s", "frac": executed * 3 / (ms * 1e-3) / fp32_peak,
+                         "note": "the group engine issues 2 instructions per update (sum-first estimate) and skips the K^2 work of every task's last step, so frac counts reference work, not issued instructions"}}
+        p4.close()
+        m4.close()
+    except Exception as e:
+        out["batched_K512_T1024"] = f"failed: {e}"
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -285,6 +373,10 @@ def run_ours(args):
                                 "executed_steps": p2.report().executed_steps}
         p2.close()
 
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = other_configs(fv, ctx, model, ob, stream, torch)
+
     rep = plan.report()
     peak, peak_src = peaks()
     fp_mean = sum(fp_ms) / len(fp_ms)
@@ -316,6 +408,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": algo_bytes},
         "model_prep_ms": model.prep_ms,
         "other_segment_counts": also,
+        "other_configs": extras,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -357,6 +450,7 @@ def main():
                          "T == 2N is broken there); N=8 and N=64 are timed beside it")
     ap.add_argument("--engine", default="auto", choices=["auto", "step", "persistent"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the parity check and the CPU baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the FLASH-BS and batched-decode side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

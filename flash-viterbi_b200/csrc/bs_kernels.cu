@@ -15,8 +15,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "flashv_internal.h"
 #include "trellis_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace flashv {
 
@@ -271,9 +275,18 @@ __device__ int bs_fix_entry(const BsArgs &a, const float *row, int i, int o, Hea
 }
 
 // dynamic shared memory: float sscore[Kp]; HeapNode beam[B] ; HeapNode node[2B+4]; BeamScratch
+//
+// One thread-block CLUSTER owns one trellis vector for all of its steps.  Scoring a step is K x B
+// dependent-latency double reads (4 MB at K=3965, B=128) — more than one SM can keep in flight — so
+// the destination states are split over the cluster's CTAs, two threads per state (half the beam
+// each).  Every CTA writes its scores into the score vector of ALL CTAs through distributed shared
+// memory; after a cluster barrier each CTA builds the beam for itself (identical inputs, identical
+// result), so nothing but the scores ever crosses SMs.  CTA 0 does the end state and the walk back.
 __global__ void __launch_bounds__(1024) k_bs_pass(const BsArgs a)
 {
     extern __shared__ float4 smem_f4[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     float *smem_f = reinterpret_cast<float *>(smem_f4);
     const int K = a.K, B = a.B, T = a.T;
     float *sscore = smem_f;
@@ -281,21 +294,26 @@ __global__ void __launch_bounds__(1024) k_bs_pass(const BsArgs a)
     HeapNode *node = beam + ((B + 1) & ~1);
     BeamScratch *bs = reinterpret_cast<BeamScratch *>(node + 2 * B + 4);
     __shared__ int s_state;
-    const int v = blockIdx.x;
-    if (v >= a.nvec) return;
+    const int v = blockIdx.x / CS;
+    if (v >= a.nvec) return;  // whole clusters leave together
     const VecDesc vd = a.vecs[v];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const int32_t *ob = a.ob + (size_t)vd.seq * T;
     int32_t *ans = a.ans + (size_t)vd.seq * T;
     const bool full = (vd.flags & VEC_FULL_RANGE) != 0;
+    const int per = (K + CS - 1) / CS;  // states per CTA
+    const int s_lo = rank * per, s_hi = min(K, s_lo + per);
+    float *peer_score[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) peer_score[r] = r < CS ? cluster.map_shared_rank(sscore, r) : sscore;
     auto keep_row = [&](int j) {  // the scores of step j are the "previous scores" of backpointer row j+1
         if (j < vd.mid || j > vd.R - 1) return;
         float *dst = a.rows + (size_t)(vd.psi_row + (j - vd.mid)) * K;
-        for (int i = tid; i < K; i += nthr) dst[i] = sscore[i];
+        for (int i = s_lo + tid; i < s_hi; i += nthr) dst[i] = sscore[i];
     };
 
     // start vector, S:411-426 (S:314-320 for the first pass).  prev < 0 is the reference's
-    // vit->A[-1][i], which aliases Pi[i].
+    // vit->A[-1][i], which aliases Pi[i].  Every CTA computes all of it.
     {
         const int prev = vd.L == 0 ? -1 : ans[vd.L - 1];
         const int o = ob[vd.L];
@@ -307,50 +325,74 @@ __global__ void __launch_bounds__(1024) k_bs_pass(const BsArgs a)
     __syncthreads();
     keep_row(vd.L);
     bool have_heap = build_beam(sscore, K, B, beam, node, bs, a.always_replay || (full && vd.R == vd.L));
+    cluster.sync();  // every CTA is done reading its start vector before anyone's step-1 scores arrive
 
     long long t_score = 0, t_beam = 0;
+    const int Bh = (B + 1) >> 1;
     for (int j = vd.L + 1; j <= vd.R; ++j) {
         const long long c0 = clock64();
         const int o = ob[j];
         const bool keep = j >= vd.mid + 1;  // S:448: payload latches at j == mid+1
-        for (int i = tid; i < K; i += nthr) {
-            const float tmp = __ldg(a.LBf + (size_t)o * a.Kp + i);  // S:439
+        // (the loop bound is rounded up to whole pairs: both threads of a pair reach the shuffles)
+        for (int li = tid >> 1; li < ((s_hi - s_lo + 15) & ~15); li += nthr >> 1) {
+            const int i = s_lo + li;
+            const bool live = i < s_hi;
+            const int half = tid & 1;
             float best = -FLT_MAX;
             int arg = -1;
             bool tie = false;
-            // S:440-446 over the beam.  The row reads are independent of the running maximum: fetch
-            // a batch of them before the compare chain consumes any.
-            constexpr int UB = 8;
-            int e0 = 0;
-            for (; e0 + UB <= B; e0 += UB) {
-                double la[UB];
+            float tmp = 0.f;
+            if (live) {
+                tmp = __ldg(a.LBf + (size_t)o * a.Kp + i);  // S:439
+                // S:440-446 over this thread's half of the beam.  The row reads are independent of the
+                // running maximum: fetch a batch of them before the compare chain consumes any.
+                constexpr int UB = 8;
+                int e0 = half ? Bh : 0;
+                const int e1 = half ? B : Bh;
+                for (; e0 + UB <= e1; e0 += UB) {
+                    double la[UB];
 #pragma unroll
-                for (int e = 0; e < UB; ++e) la[e] = __ldg(a.LAd + (size_t)beam[e0 + e].s * K + i);
+                    for (int e = 0; e < UB; ++e) la[e] = __ldg(a.LAd + (size_t)beam[e0 + e].s * K + i);
 #pragma unroll
-                for (int e = 0; e < UB; ++e) {
-                    const HeapNode h = beam[e0 + e];
-                    const float x = exact_cand(__fadd_rn(tmp, h.v), la[e]);
+                    for (int e = 0; e < UB; ++e) {
+                        const HeapNode h = beam[e0 + e];
+                        const float x = exact_cand(__fadd_rn(tmp, h.v), la[e]);
+                        tie = x > best ? false : (tie || (x == best && arg >= 0));
+                        if (x > best) best = x, arg = h.s;
+                    }
+                }
+                for (; e0 < e1; ++e0) {
+                    const HeapNode h = beam[e0];
+                    const float x = exact_cand(__fadd_rn(tmp, h.v), __ldg(a.LAd + (size_t)h.s * K + i));
                     tie = x > best ? false : (tie || (x == best && arg >= 0));
                     if (x > best) best = x, arg = h.s;
                 }
             }
-            for (; e0 < B; ++e0) {
-                const HeapNode h = beam[e0];
-                const float x = exact_cand(__fadd_rn(tmp, h.v), __ldg(a.LAd + (size_t)h.s * K + i));
-                tie = x > best ? false : (tie || (x == best && arg >= 0));
-                if (x > best) best = x, arg = h.s;
+            // the second half's result joins the first's: slot order = first half, then second half
+            const float obest = __shfl_xor_sync(FULL_MASK, best, 1);
+            const int oarg = __shfl_xor_sync(FULL_MASK, arg, 1);
+            const bool otie = __shfl_xor_sync(FULL_MASK, (int)tie, 1) != 0;
+            if (live && half == 0) {
+                if (obest > best)
+                    best = obest, arg = oarg, tie = otie;
+                else if (obest == best && oarg >= 0 && arg >= 0)
+                    tie = true;
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r < CS) peer_score[r][i] = best;
+                // with the true heap in beam[] (slot order) the first maximum IS the reference's choice
+                if (keep) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + i,
+                                    arg >= 0 && tie && !have_heap ? arg | a.flagbit : arg);
             }
-            sscore[i] = best;
-            // with the true heap in beam[] (slot order) the first maximum IS the reference's choice
-            if (keep) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + i,
-                                arg >= 0 && tie && !have_heap ? arg | a.flagbit : arg);
         }
-        __syncthreads();
+        cluster.sync();  // all scores of step j are in every CTA's vector
         const long long c1 = clock64();
         keep_row(j);
         have_heap = build_beam(sscore, K, B, beam, node, bs, a.always_replay || (full && j == vd.R));
+        cluster.sync();  // every CTA is done reading the scores of step j
         t_score += c1 - c0, t_beam += clock64() - c1;
     }
+    if (rank != 0) return;
     if (a.trace && tid == 0) a.trace[2 * v] = t_score, a.trace[2 * v + 1] = t_beam;
 
     // ---- end state: S:374-383 / S:454-463 for a full-range pass, Find_T3_State (S:73-86) otherwise ----
@@ -424,7 +466,21 @@ int bs_run_pass(flashv_plan *p, const Pass &pass)
         return FLASHV_ERR_ARG;
     }
     FV_CUDA(cudaFuncSetAttribute(k_bs_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_bs_pass<<<pass.nvec, 1024, smem, ctx->stream>>>(a);
+    // cluster size: enough CTAs that a step's K x B row reads are spread over several SMs, but no more
+    // clusters x CTAs than the GPU holds at once (one 1024-thread CTA per SM)
+    int cs = 8;
+    while (cs > 1 && ((size_t)m->K * p->B < (size_t)cs * 32768 || pass.nvec * cs > 2 * ctx->sm_count)) cs >>= 1;
+    if (const char *force = getenv("FLASHV_BS_CLUSTER")) {  // tests: 1, 2, 4 or 8 regardless of the sizes
+        const int f = atoi(force);
+        if (f == 1 || f == 2 || f == 4 || f == 8) cs = f;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)pass.nvec * cs), cfg.blockDim = dim3(1024), cfg.dynamicSmemBytes = smem, cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    FV_CUDA(cudaLaunchKernelEx(&cfg, k_bs_pass, a));
     FV_CUDA(cudaGetLastError());
     ++p->launches;
     if (a.trace) {

@@ -277,7 +277,7 @@ __global__ void k_flash_backtrack(const VecDesc *__restrict__ vecs, int nvec, co
 // The same walk for ONE long vector (the first pass: T-1-mids[0] dependent hops).  A hop through
 // global memory costs an L2 round trip (~0.5 us: 125 us for T=256); here the CTA copies a window
 // of consecutive rows into shared memory with coalesced 16-byte loads and thread 0 hops inside it.
-__global__ void __launch_bounds__(512) k_flash_backtrack_staged(const VecDesc *__restrict__ vecs, const void *__restrict__ psi,
+__global__ void __launch_bounds__(1024) k_flash_backtrack_staged(const VecDesc *__restrict__ vecs, const void *__restrict__ psi,
                                                                 int psi16, int K, int T, const uint8_t *__restrict__ ismid,
                                                                 const int32_t *__restrict__ endstate,
                                                                 int32_t *__restrict__ ans, int win_rows)
@@ -297,7 +297,17 @@ __global__ void __launch_bounds__(512) k_flash_backtrack_staged(const VecDesc *_
         const int n16 = (int)((hi - lo16 + 15) >> 4);
         const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(psi) + lo16);
         __syncthreads();  // previous window fully consumed
-        for (int t = threadIdx.x; t < n16; t += blockDim.x) swin[t] = src[t];  // reads past `hi` stay inside the store's padding
+        // 8 x 16 bytes in flight per thread: the window copy is a string of L2 round trips otherwise
+        // (reads past `hi` stay inside the store's padding)
+        for (int t0 = threadIdx.x; t0 < n16; t0 += 8 * blockDim.x) {
+            uint4 buf[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (t0 + u * blockDim.x < n16) buf[u] = src[t0 + u * blockDim.x];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (t0 + u * blockDim.x < n16) swin[t0 + u * blockDim.x] = buf[u];
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned char *base = reinterpret_cast<const unsigned char *>(swin) + (lo - lo16);
@@ -408,7 +418,7 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
     if (pass.nvec == 1 && pass.max_steps >= 16 && win_rows >= 4) {
         const size_t smem = (size_t)win_rows * row_bytes + 32;
         FV_CUDA(cudaFuncSetAttribute(k_flash_backtrack_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        k_flash_backtrack_staged<<<1, 512, smem, st>>>(vecs, p->d_psi, p->psi16, K, T, p->d_ismid, p->d_endstate, p->d_ans,
+        k_flash_backtrack_staged<<<1, 1024, smem, st>>>(vecs, p->d_psi, p->psi16, K, T, p->d_ismid, p->d_endstate, p->d_ans,
                                                       win_rows);
     } else {
         k_flash_backtrack<<<(pass.nvec + 127) / 128, 128, 0, st>>>(vecs, pass.nvec, p->d_psi, p->psi16, K, T, p->d_ismid,

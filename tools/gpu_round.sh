@@ -1,26 +1,32 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, then short bench runs.  Logs land in gpurun_out/.
+# One gpurun call for a round's evidence: GPU parity tests, smoke, both bench arms, then (each only
+# after the same command exited 0 without ncu) the ncu launch list of bench.py and full captures of
+# the dominant kernels.  Logs land in gpurun_out/; copy what is to be judged into profiles/.
 mkdir -p gpurun_out
 nvidia-smi > gpurun_out/nvidia-smi.txt 2>&1
 nproc > gpurun_out/nproc.txt
-python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
 timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
 rc=$?
 echo "pytest exit $rc" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
 if [ $rc -ne 0 ]; then echo "tests failed: skipping benches"; exit 0; fi
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
-timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_persistent_n64.log 2>&1
-timeout 120 python bench.py --steps 5 --warmup 3 --segments 8 --no-cpu > gpurun_out/bench_persistent_n8.log 2>&1
-timeout 120 python bench.py --steps 5 --warmup 3 --segments 127 --no-cpu > gpurun_out/bench_persistent_n127.log 2>&1
-timeout 120 python bench.py --steps 5 --warmup 3 --engine step --no-cpu > gpurun_out/bench_step_n64.log 2>&1
-for c in; do
-FLASHV_CHUNK=$c timeout 120 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_persistent_chunk$c.log 2>&1
-done
-tail -2 gpurun_out/smoke.log; tail -1 gpurun_out/bench_persistent_n64.log
-python tools/profile_target.py --beam 128 --segments 8 --iters 2 > gpurun_out/bs_n8_b128.log 2>&1
-python tools/profile_target.py --beam 128 --segments 1 --iters 2 >> gpurun_out/bs_n8_b128.log 2>&1
-python tools/profile_target.py --beam 32 --segments 8 --iters 2 >> gpurun_out/bs_n8_b128.log 2>&1
-cat gpurun_out/bs_n8_b128.log
-bash tools/gpu_trace.sh
+tail -2 gpurun_out/smoke.log
+timeout 600 python bench.py > gpurun_out/bench_default.log 2>&1
+echo "bench exit $?"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 0 > gpurun_out/bench_reference.log 2>&1
+timeout 120 python bench.py --steps 5 --warmup 3 --segments 8 --no-cpu --no-extras > gpurun_out/bench_persistent_n8.log 2>&1
+timeout 120 python bench.py --steps 5 --warmup 3 --segments 64 --no-cpu --no-extras > gpurun_out/bench_persistent_n64.log 2>&1
+timeout 120 python bench.py --steps 5 --warmup 3 --engine step --no-cpu --no-extras > gpurun_out/bench_step_n127.log 2>&1
+tail -c 1500 gpurun_out/bench_default.log
+B="python bench.py --steps 2 --warmup 3 --no-cpu --no-extras"
+$B > gpurun_out/plain_bench.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_bench.csv $B > gpurun_out/ncu_launch_bench.log 2>&1
+P="python tools/profile_target.py --engine persistent --segments 127 --iters 2"
+$P > gpurun_out/plain_persist.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_flash_persist -s 1 -c 1 -f -o gpurun_out/prof_persist $P > gpurun_out/ncu_persist.log 2>&1
+Q="python tools/profile_target.py --beam 128 --segments 8 --iters 1"
+$Q > gpurun_out/plain_bs.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_bs_pass -c 1 -f -o gpurun_out/prof_bs $Q > gpurun_out/ncu_bs.log 2>&1
+cat gpurun_out/plain_persist.log gpurun_out/plain_bs.log
