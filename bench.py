@@ -307,7 +307,7 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     ctx = fv.Context(local, stream.cuda_stream)
     model = fv.Model(ctx, A, B, Pi)
-    engine = {"auto": fv.ENGINE_AUTO, "step": fv.ENGINE_STEP, "persistent": fv.ENGINE_PERSISTENT}[args.engine]
+    engine = {"auto": fv.ENGINE_AUTO, "step": fv.ENGINE_STEP, "persistent": fv.ENGINE_PERSISTENT, "sparse": fv.ENGINE_SPARSE}[args.engine]
     plan = fv.Plan(model, T, args.segments, 1, 0, engine)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -395,7 +395,7 @@ def run_ours(args):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 storage, f64 exact re-check (reference arithmetic, bit-exact)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "K": K, "T": T, "M": M, "segments_N": args.segments,
-                   "executed_steps": rep.executed_steps, "engine": {1: "step", 2: "persistent"}.get(rep.engine),
+                   "executed_steps": rep.executed_steps, "engine": {1: "step", 2: "persistent", 3: "sparse"}.get(rep.engine),
                    "sequences_per_gpu": 1, "sharding": "independent sequences per GPU, no collective",
                    "l2": "flushed between decodes (256 MiB fill); the 62.9 MB log table is meant to stay L2-resident within a decode"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(T * 4), "d2h_bytes_per_step": int(T * 4 + 4),
@@ -448,7 +448,7 @@ def main():
     ap.add_argument("--segments", type=int, default=127,
                     help="MAX_THREADS of the reference = segment count N (127 is the largest the reference handles at T=256: "
                          "T == 2N is broken there); N=8 and N=64 are timed beside it")
-    ap.add_argument("--engine", default="auto", choices=["auto", "step", "persistent"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "step", "persistent", "sparse"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the parity check and the CPU baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the FLASH-BS and batched-decode side measurements")
     args = ap.parse_args()

@@ -24,7 +24,7 @@ import numpy as np
 PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "lib" / "libflashv.so"
 
-ENGINE_AUTO, ENGINE_STEP, ENGINE_PERSISTENT = 0, 1, 2
+ENGINE_AUTO, ENGINE_STEP, ENGINE_PERSISTENT, ENGINE_SPARSE = 0, 1, 2, 3
 OK, ERR_ARG, ERR_DOMAIN, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4, -5
 
 # every symbol include/flashv.h declares (tests check the .so exports all of them)

@@ -139,7 +139,7 @@ extern "C" void flashv_model_destroy(flashv_model *m)
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     for (flashv_plan *p : m->plan_cache) flashv_plan_destroy(p);
-    cudaFree(m->hiT), cudaFree(m->hiC), cudaFree(m->hiS), cudaFree(m->LAd), cudaFree(m->LBf), cudaFree(m->LBd), cudaFree(m->LPi);
+    cudaFree(m->hiT), cudaFree(m->hiC), cudaFree(m->hiS), cudaFree(m->csc_ptr), cudaFree(m->csc_k), cudaFree(m->csc_la), cudaFree(m->LAd), cudaFree(m->LBf), cudaFree(m->LBd), cudaFree(m->LPi);
     cudaFree(m->scratch_f), cudaFree(m->scratch_i), cudaFree(m->scratch_x);
     delete m;
 }
@@ -196,6 +196,12 @@ extern "C" int flashv_plan_create(flashv_model *m, int T, int N, int batch, int 
         return FLASHV_ERR_ARG;
     }
     if (engine == FLASHV_ENGINE_AUTO) engine = ctx->coop ? FLASHV_ENGINE_PERSISTENT : FLASHV_ENGINE_STEP;
+    if (engine == FLASHV_ENGINE_SPARSE && (!sparse_engine_available(m) || !ctx->coop || B > 0)) {
+        delete p;
+        set_error("flashv_plan_create: the sparse engine needs a FLASH plan, a cooperative-launch device and a model whose "
+                  "transition table is at most half non-zero with K < 65536");
+        return FLASHV_ERR_ARG;
+    }
     p->engine = engine;
     // FLASH-BS keeps one flag bit in every backpointer entry (bs_kernels.cu)
     p->psi16 = (B > 0 ? m->K < 32768 : m->K < 65535) ? 1 : 0;

@@ -367,6 +367,7 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
     if (time_it) FV_CUDA(cudaEventRecord(ctx->ev[2], st));
     const float *final_delta = d0;
     const bool persistent = p->engine == FLASHV_ENGINE_PERSISTENT && pass.nvec == 1;
+    const bool sparse = p->engine == FLASHV_ENGINE_SPARSE && pass.nvec == 1;
     // many vectors over a table small enough that the deltas of a group stay in shared memory (flash_group.cu)
     const bool grouped = p->engine != FLASHV_ENGINE_STEP && pass.nvec >= 2 * ctx->sm_count && group_engine_fits(m);
     if (!grouped) {  // the group kernel builds its start vectors itself
@@ -379,6 +380,10 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
         int rc = group_run_pass(p, pass, d1);
         if (rc != FLASHV_OK) return rc;
         final_delta = d1;
+    } else if (sparse) {
+        int rc = sparse_pass(p, pass);
+        if (rc != FLASHV_OK) return rc;
+        final_delta = d1;  // like the persistent kernel
     } else if (persistent) {
         int rc = persistent_pass(p, pass);
         if (rc != FLASHV_OK) return rc;

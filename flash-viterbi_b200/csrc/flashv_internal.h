@@ -87,6 +87,11 @@ struct flashv_model {
     int Kp = 0;               // K rounded up to a multiple of 128 (one warp x float4)
     float *hiT = nullptr;     // [K][Kp]  (float)log A, destination-major: hiT[i][k] = log A[k][i]; pad = -inf
     float *hiC = nullptr;     // K*Kp     the same, CTA-tiled for the persistent engine (tile_geom.h)
+    int *csc_ptr = nullptr;       // in-edge lists of the transition graph (flash_sparse.cu); null when the table is dense or K >= 65536
+    uint16_t *csc_k = nullptr;
+    double *csc_la = nullptr;
+    long long csc_nnz = 0;
+    int csc_max_cta_nnz = 0;
     float *hiS = nullptr;     // [Kp][Kp] the same, source-major (hiS[k][i]), for the group engine; only when Kp <= 1536
     int tile_G = 0;           // grid the tiling was built for (min(#SM, K))
     double *LAd = nullptr;    // [K][K]   log A, source-major as the reference stores A (F:27)
@@ -143,6 +148,9 @@ void build_tiled_slice(const double *LAd, float *hiC, int K, int Kp, int col_beg
 int shard_build_table(flashv_plan *p);
 
 int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it);
+int sparse_build(flashv_model *m, const double *hLA);               // flash_sparse.cu
+bool sparse_engine_available(const flashv_model *m);
+int sparse_pass(flashv_plan *p, const Pass &pass);
 bool group_engine_fits(const flashv_model *m);                       // flash_group.cu
 int group_run_pass(flashv_plan *p, const Pass &pass, float *dfinal);  // flash_group.cu
 constexpr int GROUP_MAX_KP = 1536;  // largest padded K the group engine's shared-memory buffers hold

@@ -165,7 +165,9 @@ int tables_build(flashv_model *m, const float *A, const float *B, const float *P
     TB_CUDA(cudaGetLastError());
     TB_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef TB_CUDA
+    const int sparse_rc = sparse_build(m, hLA);
     cudaFreeHost(hLA);
+    if (sparse_rc != FLASHV_OK) return sparse_rc;
     m->prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return FLASHV_OK;
 }

@@ -40,6 +40,8 @@ typedef struct flashv_plan flashv_plan;   /* decode schedule + workspace for one
 #define FLASHV_ENGINE_AUTO 0
 #define FLASHV_ENGINE_STEP 1       /* one kernel launch per trellis step */
 #define FLASHV_ENGINE_PERSISTENT 2 /* one cooperative launch per pass, TMA-fed, grid barrier per step */
+#define FLASHV_ENGINE_SPARSE 3     /* opt-in: the pass walks the in-edge lists (entries with A[k][i] == 0 can never win,
+                                      F:171), resident in shared memory; same results, not the dense roofline's bytes */
 
 typedef struct flashv_report {
     double decode_ms;          /* device time of the decode proper (CUDA events, tables resident) */

@@ -11,6 +11,14 @@ pytestmark = pytest.mark.gpu
 NEG_MAX = np.float32(-3.4028234663852886e38)
 
 
+def _engines(fv, A):
+    """Every engine that accepts this model: the sparse one needs a table at most half non-zero."""
+    eng = [fv.ENGINE_STEP, fv.ENGINE_PERSISTENT]
+    if 0 < np.count_nonzero(A) <= A.size // 2 and A.shape[0] < 65536:
+        eng.append(fv.ENGINE_SPARSE)
+    return eng
+
+
 def _bits(x):
     return np.asarray(x, np.float32).view(np.uint32)
 
@@ -44,11 +52,15 @@ def test_reference_golden_vectors(fv, oracle_mod, golden_models, name):
         assert _bits(score) == _bits(oscore), (name, case["prog"], case["N"], case["B"])
 
 
-@pytest.mark.parametrize("engine", ["STEP", "PERSISTENT"])
+@pytest.mark.parametrize("engine", ["STEP", "PERSISTENT", "SPARSE"])
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
 def test_both_engines_on_goldens(fv, golden_models, name, engine):
     eng = getattr(fv, "ENGINE_" + engine)
     model = golden_models[name]
+    if engine == "SPARSE":
+        A = load_golden(name)["A"]
+        if not 0 < np.count_nonzero(A) <= A.size // 2:
+            pytest.skip("table more than half non-zero: the sparse engine declines it")
     for case in golden_cases(name):
         if case["prog"] != 0:
             continue
@@ -110,7 +122,7 @@ def test_flash_random_models_vs_oracle(fv, oracle_mod, gpu_ctx, K, M, T, p, seed
         want, wscore, wmem = om.flash(ob, N)
         if not wscore > NEG_MAX:
             continue  # every path dead: the reference reads uninitialised trackers there
-        for eng in (fv.ENGINE_STEP, fv.ENGINE_PERSISTENT):
+        for eng in _engines(fv, A):
             plan = fv.Plan(model, T, N, 1, 0, eng)
             plan.upload(ob)
             plan.run()
@@ -340,6 +352,11 @@ def test_error_behaviour(fv, gpu_ctx):
         model.decode(np.full(16, 4, np.int32), 2)  # symbol outside [0,M)
     with pytest.raises(fv.FlashvError):
         model.decode(ob[:1], 1)  # T < 2
+    dense = fv.Model(gpu_ctx, *random_hmm(16, 4, 0.95, 52))
+    with pytest.raises(fv.FlashvError) as e:
+        fv.Plan(dense, 16, 2, 1, 0, fv.ENGINE_SPARSE)  # more than half of the table is non-zero: no edge lists
+    assert e.value.code == fv.ERR_ARG
+    dense.close()
     bad = A.copy()
     bad[0, 0] = 1.5
     with pytest.raises(fv.FlashvError) as e:
@@ -364,13 +381,14 @@ def test_headline_flash_vs_oracle(fv, headline):
     model, om, ob, A = headline
     for N in (64, 8):
         want, wscore, wmem = om.flash(ob, N)
-        for eng in (fv.ENGINE_PERSISTENT, fv.ENGINE_STEP):
+        for eng in (fv.ENGINE_PERSISTENT, fv.ENGINE_STEP, fv.ENGINE_SPARSE):
             plan = fv.Plan(model, len(ob), N, 1, 0, eng)
             plan.upload(ob)
             plan.run()
             paths, scores = plan.download()
             rep = plan.report()
             plan.close()
+            assert rep.engine == eng
             assert np.array_equal(paths[0], want), (N, eng)
             assert _bits(scores[0]) == _bits(wscore)
             assert rep.memory_bytes == wmem

@@ -16,7 +16,7 @@ from __graft_entry__ import load_pkg  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--engine", default="persistent", choices=["step", "persistent"])
+    ap.add_argument("--engine", default="persistent", choices=["step", "persistent", "sparse"])
     ap.add_argument("--segments", type=int, default=64)
     ap.add_argument("--iters", type=int, default=4)
     ap.add_argument("--K", type=int, default=3965)
@@ -31,7 +31,7 @@ def main():
     f = gen_hmm.as_reference_floats
     ctx = fv.Context(0)
     model = fv.Model(ctx, f(A), f(B), f(Pi))
-    eng = fv.ENGINE_STEP if a.engine == "step" else fv.ENGINE_PERSISTENT
+    eng = {"step": fv.ENGINE_STEP, "persistent": fv.ENGINE_PERSISTENT, "sparse": fv.ENGINE_SPARSE}[a.engine]
     plan = fv.Plan(model, a.T, a.segments, a.batch, a.beam, eng)
     obs = np.stack([gen_hmm.observations(a.T, 50, 1000 + b) for b in range(a.batch)])
     plan.upload(obs)
