@@ -229,6 +229,20 @@ def other_configs(fv, ctx, model, ob, stream, torch):
         e1.synchronize()
         return e0.elapsed_time(e1) / runs
 
+    # the same headline decode on the opt-in sparse engine (in-edge lists resident in shared memory): same
+    # results, but not the dense table's bytes, so it is reported here and never as `value`
+    try:
+        ps = fv.Plan(model, T, 127, 1, 0, fv.ENGINE_SPARSE)
+        ps.upload(ob[None, :])
+        ms = timed(ps, 5)
+        rs = ps.report()
+        out["flash_sparse_engine_N127"] = {"workload": WORKLOAD + ", N=127, ENGINE_SPARSE (edges with A[k][i] == 0 skipped: they can never win)",
+                                           "ms_per_decode": ms, "value": K * K * T / (ms * 1e-3) / 1e9, "unit": UNIT,
+                                           "first_pass_ms": rs.first_pass_ms, "us_per_step_first_pass": rs.first_pass_ms * 1e3 / (T - 1)}
+        ps.close()
+    except Exception as e:
+        out["flash_sparse_engine_N127"] = f"failed: {e}"
+
     # config 3: FLASH-BS, same model and sequence, beam 128 (latency-bound: report ms and us per sequential step)
     try:
         for n_seg in (8, 127):

@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "flashv_plan_download", "flashv_plan_report",
     "flashv_plan_shard_init", "flashv_plan_shard_buffers", "flashv_plan_shard_ipc_handles",
     "flashv_plan_shard_set_peer", "flashv_plan_shard_open_peer",
-    "flashv_trellis_init", "flashv_trellis_step", "flashv_bs_score_step", "flashv_bs_heap_replay",
+    "flashv_read_floats_cached", "flashv_trellis_init", "flashv_trellis_step", "flashv_bs_score_step", "flashv_bs_heap_replay",
     "flashv_task_list", "flashv_executed_steps", "flashv_memory_bytes", "flashv_bs_memory_bytes",
 ]
 
@@ -101,6 +101,8 @@ def lib():
     L.flashv_model_prep_ms.restype = C.c_double
     L.flashv_read_floats_text.argtypes = [C.c_char_p, C.c_long, fp]
     L.flashv_read_floats_text.restype = C.c_long
+    L.flashv_read_floats_cached.argtypes = [C.c_char_p, C.c_long, fp]
+    L.flashv_read_floats_cached.restype = C.c_long
     L.flashv_read_ints_text.argtypes = [C.c_char_p, C.c_long, ip]
     L.flashv_read_ints_text.restype = C.c_long
     L.flashv_decode.argtypes = [vp, ip, C.c_int, C.c_int, ip, fp, rp]
@@ -176,6 +178,15 @@ def bs_memory_bytes(T, N, B):
 def read_floats_text(path, n):
     out = np.empty(n, np.float32)
     got = lib().flashv_read_floats_text(os.fsencode(str(path)), n, _f(out))
+    if got != n:
+        raise IOError(f"{path}: wanted {n} floats, got {got}")
+    return out
+
+
+def read_floats_cached(path, n):
+    """read_floats_text through the binary side-car <path>.f32cache (written on the first parse)."""
+    out = np.empty(n, np.float32)
+    got = lib().flashv_read_floats_cached(os.fsencode(str(path)), n, _f(out))
     if got != n:
         raise IOError(f"{path}: wanted {n} floats, got {got}")
     return out

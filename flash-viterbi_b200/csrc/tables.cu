@@ -17,6 +17,9 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <thread>
@@ -176,6 +179,72 @@ int tables_build(flashv_model *m, const float *A, const float *B, const float *P
 
 // Program-shell ingest, F:56-95: every probability goes through fscanf("%f") into a float, i.e.
 // strtof — one rounding from the decimal text.  Read the file whole and walk it with strtof.
+// Large float files (A is K*K values, 300 MB of text at K=3965) are cut at whitespace into one piece
+// per host thread: a counting pass finds how many tokens each piece holds, then the pieces are
+// converted in parallel into their slots — the same strtof on the same characters, so the values
+// are bit-identical to the serial walk.
+static bool is_space(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+
+static long parse_floats_parallel(char *buf, size_t size, long n, float *out)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    int nthr = (int)(hw ? hw : 4);
+    if (nthr > 64) nthr = 64;
+    std::vector<size_t> cut((size_t)nthr + 1, size);
+    cut[0] = 0;
+    for (int t = 1; t < nthr; ++t) {
+        size_t p = size / nthr * t;
+        while (p < size && !is_space(buf[p])) ++p;  // never split a token
+        cut[t] = p;
+    }
+    std::vector<long> count((size_t)nthr, 0);
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthr; ++t)
+            pool.emplace_back([&, t]() {
+                long c = 0;
+                bool in = false;
+                for (size_t p = cut[t]; p < cut[t + 1]; ++p) {
+                    const bool sp = is_space(buf[p]);
+                    if (!sp && !in) ++c;
+                    in = !sp;
+                }
+                count[t] = c;
+            });
+        for (auto &th : pool) th.join();
+    }
+    std::vector<long> first((size_t)nthr + 1, 0);
+    for (int t = 0; t < nthr; ++t) first[t + 1] = first[t] + count[t];
+    std::vector<long> done((size_t)nthr, 0);
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthr; ++t)
+            pool.emplace_back([&, t]() {
+                char *p = buf + cut[t], *end = nullptr;
+                char *stop = buf + cut[t + 1];
+                const char saved = *stop;  // pieces end on whitespace or at the terminating NUL
+                (void)saved;
+                long c = 0;
+                while (p < stop && first[t] + c < n) {
+                    const float v = strtof(p, &end);
+                    if (end == p || end > stop) break;  // not a number: the serial walk would stop here too
+                    out[first[t] + c] = v;
+                    p = end;
+                    ++c;
+                    while (p < stop && is_space(*p)) ++p;
+                }
+                done[t] = c;
+            });
+        for (auto &th : pool) th.join();
+    }
+    long total = 0;
+    for (int t = 0; t < nthr; ++t) {
+        total += done[t];
+        if (done[t] != count[t] && first[t] + done[t] < n) break;  // a malformed token: everything after it is unread
+    }
+    return total < n ? total : n;
+}
+
 static long read_text(const char *path, long n, float *fout, int32_t *iout)
 {
     FILE *fp = fopen(path, "rb");
@@ -196,6 +265,11 @@ static long read_text(const char *path, long n, float *fout, int32_t *iout)
     fclose(fp);
     buf[got] = 0;
     long cnt = 0;
+    if (fout && n >= (1 << 20)) {
+        cnt = parse_floats_parallel(buf, got, n, fout);
+        free(buf);
+        return cnt;
+    }
     char *p = buf, *end = nullptr;
     while (cnt < n) {
         if (fout) {
@@ -216,3 +290,43 @@ static long read_text(const char *path, long n, float *fout, int32_t *iout)
 
 extern "C" long flashv_read_floats_text(const char *path, long n, float *out) { return read_text(path, n, out, nullptr); }
 extern "C" long flashv_read_ints_text(const char *path, long n, int32_t *out) { return read_text(path, n, nullptr, out); }
+
+// Binary side-car of a text table: the text stays canonical, <path>.f32cache holds the
+// float32 values one parse of it gave, valid as long as the text file's size and mtime are the ones
+// recorded in the header.  Anything wrong with the cache (missing, stale, short, unwritable
+// directory) silently falls back to parsing the text.
+struct CacheHeader {
+    char magic[8];  // "FLASHVC1"
+    long long n, text_size, text_mtime_ns;
+};
+
+extern "C" long flashv_read_floats_cached(const char *path, long n, float *out)
+{
+    struct stat st;
+    if (stat(path, &st) != 0) {
+        flashv::set_error("cannot open %s", path);
+        return FLASHV_ERR_ARG;
+    }
+    const long long mtime_ns = (long long)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec;
+    const std::string cpath = std::string(path) + ".f32cache";
+    if (FILE *fp = fopen(cpath.c_str(), "rb")) {
+        CacheHeader h;
+        bool ok = fread(&h, sizeof(h), 1, fp) == 1 && memcmp(h.magic, "FLASHVC1", 8) == 0 && h.n == n &&
+                  h.text_size == (long long)st.st_size && h.text_mtime_ns == mtime_ns;
+        ok = ok && fread(out, sizeof(float), (size_t)n, fp) == (size_t)n;
+        fclose(fp);
+        if (ok) return n;
+    }
+    const long got = read_text(path, n, out, nullptr);
+    if (got == n) {
+        const std::string tmp = cpath + ".tmp" + std::to_string((long long)getpid());
+        if (FILE *fp = fopen(tmp.c_str(), "wb")) {
+            CacheHeader h;
+            memcpy(h.magic, "FLASHVC1", 8);
+            h.n = n, h.text_size = (long long)st.st_size, h.text_mtime_ns = mtime_ns;
+            const bool ok = fwrite(&h, sizeof(h), 1, fp) == 1 && fwrite(out, sizeof(float), (size_t)n, fp) == (size_t)n;
+            if (fclose(fp) != 0 || !ok || rename(tmp.c_str(), cpath.c_str()) != 0) remove(tmp.c_str());
+        }
+    }
+    return got;
+}

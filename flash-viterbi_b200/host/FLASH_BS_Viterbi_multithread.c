@@ -48,18 +48,34 @@ static void die(const char *what)
     exit(1);
 }
 
-/* File naming of S:217-223: <data_path><kind>_K<K>_T<T>_prob<p>.txt */
+/* File naming of S:217-223: <data_path><kind>_K<K>_T<T>_prob<p>.txt.  If that file does not exist the
+ * DAG generator's naming is tried (generate_data/data_script_dag.py:63-66: <kind>_K<K>_T<T>_DAG.txt). */
 static const char *getAddress(const char *stype)
 {
     static char path[512];
     snprintf(path, sizeof(path), "%s%s_K%d_T%d_prob%.3f.txt", data_path, stype, K_STATE, obserRouteLEN, prob);
-    return path;
+    FILE *probe = fopen(path, "rb");
+    if (probe) {
+        fclose(probe);
+        return path;
+    }
+    static char dag[512];
+    snprintf(dag, sizeof(dag), "%s%s_K%d_T%d_DAG.txt", data_path, stype, K_STATE, obserRouteLEN);
+    probe = fopen(dag, "rb");
+    if (probe) {
+        fclose(probe);
+        return dag;
+    }
+    return path; /* neither exists: report the reference's name */
 }
 
+/* The text files stay canonical; FLASHV_TEXT_CACHE=0 turns the binary side-car (<file>.f32cache) off. */
 static void load_floats(const char *stype, long n, float *dst)
 {
     const char *p = getAddress(stype);
-    if (flashv_read_floats_text(p, n, dst) != n) {
+    const char *e = getenv("FLASHV_TEXT_CACHE");
+    const int cached = !(e && e[0] == '0');
+    if ((cached ? flashv_read_floats_cached(p, n, dst) : flashv_read_floats_text(p, n, dst)) != n) {
         fprintf(stderr, "Error reading %ld values from %s\n", n, p);
         exit(1);
     }

@@ -83,6 +83,10 @@ double flashv_model_prep_ms(const flashv_model *model); /* host log tables + upl
 /* Program-shell loader (F:56-95): fscanf("%f") / fscanf("%d") semantics. Returns count read or <0. */
 long flashv_read_floats_text(const char *path, long n, float *out);
 long flashv_read_ints_text(const char *path, long n, int32_t *out);
+/* The same values through a binary side-car (<path>.f32cache, written after the first parse and valid while the
+ * text file's size and mtime are unchanged).  The text stays canonical (data_script.py:98-101); parsing K*K
+ * decimal numbers is what dominates a run of the reference-shaped program (seconds against a millisecond decode). */
+long flashv_read_floats_cached(const char *path, long n, float *out);
 
 /* ---- one-call decodes: replace calc() ------------------------------------------------ */
 /* FLASH, calc() of F:338-368.  ob[T] in [0,M); N = MAX_THREADS (the segment count).

@@ -53,6 +53,38 @@ def test_text_loader_is_fscanf_compatible(fv, oracle_mod, tmp_path):
         fv.read_floats_text(p, vals.size + 5)
 
 
+def test_parallel_parse_and_binary_cache(fv, oracle_mod, tmp_path):
+    """Large float files are parsed in parallel pieces and may be served from a binary side-car
+    (SURVEY 8f-2); both must give exactly the values of a serial fscanf("%f") walk, and the cache
+    must notice when the text changes."""
+    import os
+    import time
+
+    rng = np.random.RandomState(3)
+    n = (1 << 20) + 4321  # above the parallel-parse threshold
+    vals = rng.uniform(0, 1, n) * (rng.uniform(0, 1, n) < 0.3)
+    p = tmp_path / "A_big.txt"
+    with open(p, "w") as f:
+        for r in range(0, n, 997):  # ragged rows, like np.savetxt of a matrix with a remainder
+            f.write(" ".join("%.16f" % v for v in vals[r:r + 997]) + "\n")
+    want = np.array([float("%.16f" % v) for v in vals]).astype(np.float32)
+    a = fv.read_floats_text(p, n)
+    assert a.tobytes() == want.tobytes()
+    assert oracle_mod.read_floats(p, 5000).tobytes() == a[:5000].tobytes()  # the literal fscanf walk agrees
+    with pytest.raises(IOError):
+        fv.read_floats_text(p, n + 1)
+    c1 = fv.read_floats_cached(p, n)
+    assert (tmp_path / "A_big.txt.f32cache").exists() and c1.tobytes() == a.tobytes()
+    c2 = fv.read_floats_cached(p, n)  # served from the side-car
+    assert c2.tobytes() == a.tobytes()
+    time.sleep(0.01)
+    with open(p, "r+") as f:  # same size, different content, newer mtime
+        f.write("0.5000000000000000")
+    os.utime(p, None)
+    c3 = fv.read_floats_cached(p, n)
+    assert c3[0] == np.float32(0.5) and c3[1:].tobytes() == a[1:].tobytes()
+
+
 def _ord(x):
     b = x.view(np.int32).astype(np.int64)
     return np.where(b >= 0, b, -(b & 0x7FFFFFFF))
