@@ -17,6 +17,8 @@
 
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "flashv_internal.h"
 #include "trellis_common.cuh"
 
@@ -147,6 +149,11 @@ __device__ void heap_replay_warp(const float *score, int K, int B, HeapNode *nod
     __syncwarp();
 }
 
+// 1024 threads x 8 row reads in flight each.  (512 threads x 32 reads — the same bytes in flight with
+// fewer, fatter threads — measured 35 % slower in the scoring phase: two rounds of states per CTA and
+// register spills.)
+constexpr int BS_THREADS = 1024;
+
 struct BsArgs {
     const double *LAd, *LBd, *LPi;
     const float *LBf;
@@ -182,6 +189,7 @@ struct BsArgs {
 // Nothing is approximated: the fast path is taken only where it provably equals the replay.
 struct BeamScratch {
     int hist[256];
+    int wsum[8];
     unsigned prefix;
     int need, count, ambiguous;
 };
@@ -210,32 +218,33 @@ __device__ bool build_beam(const float *sscore, int K, int B, HeapNode *beam, He
                 if ((u & himask) == prefix) atomicAdd(&bs->hist[(u >> shift) & 255], 1);
             }
             __syncthreads();
-            if (tid < 32) {
-                // bins from the top: the bin holding the need-th largest key
-                int need = bs->need, found = -1, above = 0;
-                for (int hi = 255; hi >= 0 && found < 0; hi -= 32) {
-                    const int b = hi - tid;  // lane 0 owns the highest bin of this group
-                    const int c = bs->hist[b];
-                    int incl = c;  // inclusive prefix over lanes 0..tid (bins hi .. b)
+            // bins from the top: thread t looks at bin 255-t; an inclusive scan over the threads gives
+            // every bin the number of keys in bins above it, and exactly one bin straddles `need`
+            {
+                const int need = bs->need;
+                int c = 0, incl = 0;
+                if (tid < 256) {
+                    c = bs->hist[255 - tid];
+                    incl = c;
 #pragma unroll
                     for (int off = 1; off < 32; off <<= 1) {
                         const int t = __shfl_up_sync(FULL_MASK, incl, off);
-                        if (tid >= off) incl += t;
+                        if ((tid & 31) >= off) incl += t;
                     }
-                    const unsigned hit = __ballot_sync(FULL_MASK, above + incl >= need);
-                    if (hit) {
-                        const int l = __ffs(hit) - 1;
-                        found = hi - l;
-                        const int before = __shfl_sync(FULL_MASK, incl - c, l);  // keys in higher bins of this group
-                        need -= above + before;
-                    } else {
-                        above += __shfl_sync(FULL_MASK, incl, 31);
-                    }
+                    if ((tid & 31) == 31) bs->wsum[tid >> 5] = incl;
                 }
-                if (tid == 0) {
-                    bs->prefix = prefix | (unsigned)found << shift;
-                    bs->need = need;
-                    if (pass == 3) bs->ambiguous = bs->hist[found] != need;  // several scores == tau and not all fit
+                __syncthreads();
+                if (tid < 256) {
+                    int above = 0;  // keys in the bins of earlier warps
+#pragma unroll
+                    for (int w = 0; w < 8; ++w)
+                        if (w < (tid >> 5)) above += bs->wsum[w];
+                    const int before = above + incl - c;  // keys in bins strictly above this one
+                    if (before < need && before + c >= need) {
+                        bs->prefix = prefix | (unsigned)(255 - tid) << shift;
+                        bs->need = need - before;
+                        if (pass == 3) bs->ambiguous = c != need - before;  // several scores == tau and not all fit
+                    }
                 }
             }
             __syncthreads();
@@ -282,7 +291,7 @@ __device__ int bs_fix_entry(const BsArgs &a, const float *row, int i, int o, Hea
 // each).  Every CTA writes its scores into the score vector of ALL CTAs through distributed shared
 // memory; after a cluster barrier each CTA builds the beam for itself (identical inputs, identical
 // result), so nothing but the scores ever crosses SMs.  CTA 0 does the end state and the walk back.
-__global__ void __launch_bounds__(1024) k_bs_pass(const BsArgs a)
+__global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
 {
     extern __shared__ float4 smem_f4[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -346,27 +355,25 @@ __global__ void __launch_bounds__(1024) k_bs_pass(const BsArgs a)
                 tmp = __ldg(a.LBf + (size_t)o * a.Kp + i);  // S:439
                 // S:440-446 over this thread's half of the beam.  The row reads are independent of the
                 // running maximum: fetch a batch of them before the compare chain consumes any.
-                constexpr int UB = 8;
                 int e0 = half ? Bh : 0;
                 const int e1 = half ? B : Bh;
-                for (; e0 + UB <= e1; e0 += UB) {
-                    double la[UB];
+                auto batch = [&](auto ub) {  // ub() row reads in flight, then the compare chain
+                    constexpr int UB = decltype(ub)::value;
+                    for (; e0 + UB <= e1; e0 += UB) {
+                        double la[UB];
 #pragma unroll
-                    for (int e = 0; e < UB; ++e) la[e] = __ldg(a.LAd + (size_t)beam[e0 + e].s * K + i);
+                        for (int e = 0; e < UB; ++e) la[e] = __ldg(a.LAd + (size_t)beam[e0 + e].s * K + i);
 #pragma unroll
-                    for (int e = 0; e < UB; ++e) {
-                        const HeapNode h = beam[e0 + e];
-                        const float x = exact_cand(__fadd_rn(tmp, h.v), la[e]);
-                        tie = x > best ? false : (tie || (x == best && arg >= 0));
-                        if (x > best) best = x, arg = h.s;
+                        for (int e = 0; e < UB; ++e) {
+                            const HeapNode h = beam[e0 + e];
+                            const float x = exact_cand(__fadd_rn(tmp, h.v), la[e]);
+                            tie = x > best ? false : (tie || (x == best && arg >= 0));
+                            if (x > best) best = x, arg = h.s;
+                        }
                     }
-                }
-                for (; e0 < e1; ++e0) {
-                    const HeapNode h = beam[e0];
-                    const float x = exact_cand(__fadd_rn(tmp, h.v), __ldg(a.LAd + (size_t)h.s * K + i));
-                    tie = x > best ? false : (tie || (x == best && arg >= 0));
-                    if (x > best) best = x, arg = h.s;
-                }
+                };
+                batch(std::integral_constant<int, 8>());
+                batch(std::integral_constant<int, 1>());
             }
             // the second half's result joins the first's: slot order = first half, then second half
             const float obest = __shfl_xor_sync(FULL_MASK, best, 1);
@@ -467,7 +474,7 @@ int bs_run_pass(flashv_plan *p, const Pass &pass)
     }
     FV_CUDA(cudaFuncSetAttribute(k_bs_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // cluster size: enough CTAs that a step's K x B row reads are spread over several SMs, but no more
-    // clusters x CTAs than the GPU holds at once (one 1024-thread CTA per SM)
+    // clusters x CTAs than the GPU holds at once
     int cs = 8;
     while (cs > 1 && ((size_t)m->K * p->B < (size_t)cs * 32768 || pass.nvec * cs > 2 * ctx->sm_count)) cs >>= 1;
     if (const char *force = getenv("FLASHV_BS_CLUSTER")) {  // tests: 1, 2, 4 or 8 regardless of the sizes
@@ -475,7 +482,7 @@ int bs_run_pass(flashv_plan *p, const Pass &pass)
         if (f == 1 || f == 2 || f == 4 || f == 8) cs = f;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)pass.nvec * cs), cfg.blockDim = dim3(1024), cfg.dynamicSmemBytes = smem, cfg.stream = ctx->stream;
+    cfg.gridDim = dim3((unsigned)pass.nvec * cs), cfg.blockDim = dim3(BS_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
