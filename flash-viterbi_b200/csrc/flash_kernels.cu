@@ -399,7 +399,10 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
             // on their last step and (unless the pass is full-range) need a single column
             const int n_act = pass.nactive[s];
             const int n_cont = pass.full_range ? n_act : pass.nactive[s + 1];
-            if (n_cont > 0) {
+            if (n_cont > 0 && p->engine == FLASHV_ENGINE_SPARSE) {
+                int rc = sparse_level_step(p, pass, s, n_cont, a.din, a.dout);
+                if (rc != FLASHV_OK) return rc;
+            } else if (n_cont > 0) {
                 a.nact = n_cont;
                 FV_CUDA(dispatch_step(a, n_cont, ctx->sm_count, st));
                 ++p->launches;

@@ -150,6 +150,109 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_flash_sparse_pass(const Spars
     }
 }
 
+// ---- one step of a level of the task tree (many vectors) over the same edge lists -----------------
+// grid (column workers, vector groups): a CTA stages delta of SQ vectors in shared memory and its
+// warps walk destination columns; a column's edge list is read once (coalesced) and applied to all
+// SQ vectors with the exact chain, first maximum kept lane-locally in ascending k.
+constexpr int SQ = 8;  // vectors per group
+
+struct SparseStepArgs {
+    const int *cptr;
+    const uint16_t *ck;
+    const double *cla;
+    const float *LBf;
+    int K, Kp;
+    const VecDesc *vecs;
+    int nact, s;
+    const float *din;
+    float *dout;
+    const int32_t *ob;
+    int T;
+    void *psi;
+    int psi16;
+};
+
+__global__ void __launch_bounds__(512) k_flash_sparse_step(const SparseStepArgs a)
+{
+    extern __shared__ float4 sp_sdelta4[];
+    float *sdelta = reinterpret_cast<float *>(sp_sdelta4);  // [SQ][Kp]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int v0 = blockIdx.y * SQ;
+    const int Kp4 = a.Kp >> 2;
+#pragma unroll
+    for (int q = 0; q < SQ; ++q) {
+        const bool live = v0 + q < a.nact;
+        const float4 *src = reinterpret_cast<const float4 *>(a.din + (size_t)(v0 + q) * a.Kp);
+        for (int t = tid; t < Kp4; t += blockDim.x) sp_sdelta4[q * Kp4 + t] = live ? src[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    int jj[SQ], row[SQ];
+    const float *tmp_row[SQ];
+#pragma unroll
+    for (int q = 0; q < SQ; ++q) {
+        jj[q] = 0, row[q] = -1, tmp_row[q] = a.LBf;
+        if (v0 + q < a.nact) {
+            const VecDesc vd = a.vecs[v0 + q];
+            jj[q] = vd.L + a.s;
+            tmp_row[q] = a.LBf + (size_t)a.ob[(size_t)vd.seq * a.T + jj[q]] * a.Kp;  // F:233
+            if (jj[q] >= vd.mid + 1) row[q] = vd.psi_row + (jj[q] - vd.mid - 1);     // F:242
+        }
+    }
+    __syncthreads();
+    for (int i = blockIdx.x * nwarp + warp; i < a.K; i += gridDim.x * nwarp) {
+        float tmp[SQ];
+        Best b[SQ];
+#pragma unroll
+        for (int q = 0; q < SQ; ++q) tmp[q] = __ldg(tmp_row[q] + i), b[q] = Best{-FLT_MAX, 0x7fffffff};
+        const int e0 = a.cptr[i], e1 = a.cptr[i + 1];
+#pragma unroll 2
+        for (int e = e0 + lane; e < e1; e += 32) {
+            const int k = __ldg(a.ck + e);
+            const double la = __ldg(a.cla + e);
+#pragma unroll
+            for (int q = 0; q < SQ; ++q) {
+                const float x = exact_cand(__fadd_rn(tmp[q], sdelta[q * a.Kp + k]), la);  // F:236
+                if (x > b[q].x) b[q].x = x, b[q].k = k;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < SQ; ++q) {
+            if (v0 + q >= a.nact) continue;  // warp-uniform: padding vector of the last group
+            Best r = warp_best(b[q]);
+            if (!(r.x > -FLT_MAX)) r.x = -FLT_MAX, r.k = -1;
+            if (lane == 0) {
+                a.dout[(size_t)(v0 + q) * a.Kp + i] = r.x;
+                if (row[q] >= 0) psi_store(a.psi, a.psi16, (size_t)row[q] * a.K + i, r.k);
+            }
+        }
+    }
+}
+
+int sparse_level_step(flashv_plan *p, const Pass &pass, int s, int nact, const float *din, float *dout)
+{
+    flashv_model *m = p->model;
+    flashv_ctx *ctx = m->ctx;
+    SparseStepArgs a;
+    a.cptr = m->csc_ptr, a.ck = m->csc_k, a.cla = m->csc_la, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+    a.vecs = p->d_vecs + pass.vec_offset, a.nact = nact, a.s = s, a.din = din, a.dout = dout;
+    a.ob = p->d_ob, a.T = p->T, a.psi = p->d_psi, a.psi16 = p->psi16;
+    const size_t smem = (size_t)SQ * m->Kp * sizeof(float);
+    if (smem > (size_t)ctx->smem_optin) {
+        set_error("sparse engine: K=%d does not fit the level kernel's shared memory", m->K);
+        return FLASHV_ERR_ARG;
+    }
+    FV_CUDA(cudaFuncSetAttribute(k_flash_sparse_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ngroups = (nact + SQ - 1) / SQ;
+    int per_sm = (int)((size_t)ctx->smem_optin / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    int workers = (ctx->sm_count * per_sm) / ngroups;
+    const int max_workers = (m->K + 15) / 16;  // 16 warps per CTA, at least one column each
+    workers = workers < 1 ? 1 : (workers > max_workers ? max_workers : workers);
+    k_flash_sparse_step<<<dim3(workers, ngroups), 512, smem, ctx->stream>>>(a);
+    FV_CUDA(cudaGetLastError());
+    ++p->launches;
+    return FLASHV_OK;
+}
+
 // ---- host side: the in-edge lists, built once per model from the host log table -------------------
 int sparse_build(flashv_model *m, const double *hLA)
 {

@@ -151,6 +151,7 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it);
 int sparse_build(flashv_model *m, const double *hLA);               // flash_sparse.cu
 bool sparse_engine_available(const flashv_model *m);
 int sparse_pass(flashv_plan *p, const Pass &pass);
+int sparse_level_step(flashv_plan *p, const Pass &pass, int s, int nact, const float *din, float *dout);
 bool group_engine_fits(const flashv_model *m);                       // flash_group.cu
 int group_run_pass(flashv_plan *p, const Pass &pass, float *dfinal);  // flash_group.cu
 constexpr int GROUP_MAX_KP = 1536;  // largest padded K the group engine's shared-memory buffers hold
