@@ -281,6 +281,14 @@ def other_configs(fv, ctx, model, ob, stream, torch):
                          "peak": fp32_peak / 1e12, "unit": "T lane-op/s", "frac": executed * 3 / (ms * 1e-3) / fp32_peak,
                          "note": "the group engine issues 2 instructions per update (sum-first estimate) and skips the K^2 work of every task's last step, so frac counts reference work, not issued instructions"}}
         p4.close()
+        # the same batch at the largest segment count the reference accepts at T=1024: every task is one or two
+        # steps long and a task's last step needs one column, so the tree costs almost nothing
+        p5 = fv.Plan(m4, T4, 511, B4, 0, fv.ENGINE_AUTO)
+        p5.upload(obs4)
+        ms5 = timed(p5, 2)
+        out["batched_K512_T1024"]["N511"] = {"ms_per_batch": ms5, "value": B4 * float(K4) * K4 * T4 / (ms5 * 1e-3) / 1e9,
+                                              "executed_steps_per_sequence": p5.report().executed_steps}
+        p5.close()
         m4.close()
     except Exception as e:
         out["batched_K512_T1024"] = f"failed: {e}"

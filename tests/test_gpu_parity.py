@@ -267,6 +267,41 @@ def test_config4_shape_group_engine(fv, oracle_mod, gpu_ctx):
     model.close()
 
 
+def test_config4_full_size_batch(fv, oracle_mod, gpu_ctx):
+    """BASELINE config 4 at its full size on one GPU: 8192 sequences, K=512, T=1024, at N=32 and at
+    the largest segment count the reference accepts (N=511).  The oracle decodes a sample of the
+    sequences outright at both N; every sequence is checked through size-independent properties:
+    its path only uses transitions and emissions that exist, and the score (the full-range pass's
+    maximum, the same computation for every N > 2) has the same bits at both N.  The PATHS need not
+    agree between the two N: every task restarts from Ans[L-1] with its own float rounding (F:220),
+    so near-ties resolve differently — the reference itself decodes about a fifth of these sequences
+    to different, equally scored paths (tools/n_dependence.py), and the kernels reproduce that."""
+    K, M, T, NSEQ = 512, 50, 1024, 8192
+    A, B, Pi = random_hmm(K, M, 0.253, 1)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    obs = np.random.RandomState(4).randint(0, M, (NSEQ, T)).astype(np.int32)
+    scores_by_n = {}
+    try:
+        for N in (32, 511):
+            plan = fv.Plan(model, T, N, NSEQ, 0, fv.ENGINE_AUTO)
+            plan.upload(obs)
+            plan.run()
+            paths, scores = plan.download()
+            plan.close()
+            scores_by_n[N] = scores
+            assert paths.min() >= 0 and paths.max() < K
+            assert (A[paths[:, :-1], paths[:, 1:]] > 0).all()  # every transition taken exists
+            assert (B[paths, obs] > 0).all()                    # every emission is possible
+            for b in (1, 4097, NSEQ - 1):  # sequence 1 is one whose path differs between the two N
+                want, wscore, _ = om.flash(obs[b], N)
+                assert np.array_equal(paths[b], want), (N, b)
+                assert _bits(scores[b]) == _bits(wscore)
+        assert np.array_equal(_bits(scores_by_n[32]), _bits(scores_by_n[511]))
+    finally:
+        model.close()
+
+
 def test_wide_model_multi_round(fv, oracle_mod, gpu_ctx):
     """K large enough that a persistent CTA owns more columns than one round (28) and a chain is
     longer than a warp (K > 4096): the general paths of the window scan."""

@@ -1,8 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 -p no:cacheprovider -k "config4" --durations=3 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
-for n in 127 64 32 16 8 1; do
-timeout 120 python tools/profile_target.py --engine sparse --iters 4 --segments $n
-done
+tail -8 gpurun_out/pytest_gpu.log
