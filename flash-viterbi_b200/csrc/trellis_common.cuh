@@ -63,6 +63,29 @@ __device__ __forceinline__ float warp_max(float v)
     return v;
 }
 
+// Window threshold for the sum-first estimate.  For source k let R = tmp + delta[k] + logA[k][i]
+// (reals; all three <= 0) and U the float spacing at |R|.  The reference's candidate (F:170) is
+//     cand = fl32( fl64( fl32(tmp + delta[k]) + logA ) ):  two float roundings of sums no larger in
+//            magnitude than R (U/2 each; U if the last one crosses into the next binade) plus a
+//            double rounding (2^-29 U)                                  |cand - R|      <= 1.5 U + eps
+// and the kernel's estimate is m2 = fl32(delta[k] + fl32(logA)), again two roundings of at most
+// U/2:                                                                  |m2 + tmp - R|  <= 1 U
+// so |cand - (m2 + tmp)| <= 2.5 U + eps (1.5 U observed, tests/test_host_logic.py).  If k* is the
+// reference's argmax and kt the argmax of m2:
+//     m2(k*) + tmp >= cand(k*) - 2.5U >= cand(kt) - 2.5U >= m2(kt) + tmp - 5U.
+// Candidates near the top may sit one binade above c = fl32(top + tmp), where the spacing doubles,
+// so with G = the spacing at |c|:  m2(k*) >= top - 10 G - eps.  The threshold is top - 12 G, formed
+// with one rounding (error <= G/2).  Ties of cand are all inside the window, so the lowest index
+// among equal maxima is found by the exact re-evaluation, as the reference's strict '>' does.
+__device__ __forceinline__ float filter_threshold(float top, float tmp)
+{
+    const float c = __fadd_rn(top, tmp);
+    int e = (__float_as_int(c) >> 23) & 0xff;
+    e = max(e - 23, 1);
+    const float G = __int_as_float(e << 23);
+    return __fmaf_rn(-12.0f, G, top);
+}
+
 // Backpointer store: 16-bit rows when K < 65535 (0xFFFF = dead), else 32-bit.
 __device__ __forceinline__ void psi_store(void *base, int psi16, size_t idx, int v)
 {

@@ -1,5 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 -p no:cacheprovider -k "config4" --durations=3 > gpurun_out/pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -8 gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+for n in 127 127 64; do
+timeout 120 python tools/profile_target.py --engine persistent --iters 6 --segments $n
+done
+FLASHV_TMEM=0 timeout 120 python tools/profile_target.py --engine persistent --iters 6 --segments 127
