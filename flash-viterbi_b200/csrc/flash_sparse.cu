@@ -258,6 +258,8 @@ int sparse_build(flashv_model *m, const double *hLA)
 {
     const int K = m->K;
     if (K >= 65536) return FLASHV_OK;  // 16-bit source indices: larger models keep the dense engines only
+    if (const char *e = getenv("FLASHV_NO_SPARSE"))
+        if (atoi(e) != 0) return FLASHV_OK;  // skip the edge lists (saves their build time and memory on very large models)
     std::vector<int> ptr((size_t)K + 1, 0);
     for (int k = 0; k < K; ++k) {
         const double *row = hLA + (size_t)k * K;

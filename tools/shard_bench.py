@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--N", type=int, default=16)
     ap.add_argument("--p", type=float, default=0.02)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--oracle-T", type=int, default=0, help="also decode a prefix of this many observations (N=2) and compare with the oracle")
     a = ap.parse_args()
     import gen_hmm
 
@@ -39,6 +40,17 @@ def main():
     ctxs = [fv.Context(r) for r in range(ngpu)]
     models = [fv.Model(c, A, B, Pi) for c in ctxs]
     print(f"model prep {models[0].prep_ms:.0f} ms per GPU", flush=True)
+    if a.oracle_T >= 2:
+        # sub-sampled parity at the big shape: a short prefix the CPU oracle can still decode
+        from oracle import oracle
+
+        t0 = time.time()
+        om = oracle.OracleModel(A, B, Pi)
+        want, wscore, _ = om.flash(ob[:a.oracle_T], 2)
+        got, score, _ = models[0].decode(ob[:a.oracle_T], 2)
+        ok = bool(np.array_equal(got, want) and np.float32(score).view(np.uint32) == np.float32(wscore).view(np.uint32))
+        print(f"oracle check on the first {a.oracle_T} observations (N=2): path and score bits equal: {ok} ({time.time() - t0:.1f} s)", flush=True)
+        del om
     base_path = None
     out = {}
     world = 1
