@@ -190,25 +190,32 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
 // nvviter() ends with Ans[mid] = T2[cur][Ans[R]] (F:248, F:261): of the K values the last step
 // computes, only the backpointer of destination state Ans[R] is ever read (delta of the last step
 // is only needed by full-range passes, F:249-259).  So a task's last step is K updates, not K^2 —
-// and half of all tasks are one step long.  One warp per vector; same estimate / window / exact
-// logic as every other kernel.
-__global__ void __launch_bounds__(128) k_flash_last_column(const StepArgs a, int v_begin, const int32_t *__restrict__ ans)
+// and half of all tasks are one step long.  One CTA of LC_WARPS warps per vector: the column and the
+// vector are two 16 KB streams and the kernel is a chain of L2 round trips, so the more lanes share
+// them the shorter it gets.  Warp w takes the float4 groups t = 32*(w + LC_WARPS*m) + lane, i.e. the
+// elements u = w, w + LC_WARPS, ... of every chain (lane, component) of trellis_common.cuh; same
+// estimate / window / exact logic as every other kernel, combined across warps in shared memory.
+constexpr int LC_WARPS = 8;
+__global__ void __launch_bounds__(LC_WARPS * 32) k_flash_last_column(const StepArgs a, int v_begin, const int32_t *__restrict__ ans)
 {
-    const int lane = threadIdx.x & 31;
-    const int v = v_begin + blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (v >= a.nact) return;  // a.nact: one past the last vector on its final step
+    __shared__ float s_top[LC_WARPS];
+    __shared__ float s_bx[LC_WARPS];
+    __shared__ int s_bk[LC_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = v_begin + blockIdx.x;  // a.nact: one past the last vector on its final step
     const VecDesc vd = a.vecs[v];
     const int j = vd.L + a.s;  // == vd.R
     const int e = ans[(size_t)vd.seq * a.T + vd.R];
-    if (e < 0 || e >= a.K) return;
+    if (e < 0 || e >= a.K) return;  // CTA-uniform
     const float tmp = __ldg(a.LBf + (size_t)a.ob[(size_t)vd.seq * a.T + j] * a.Kp + e);  // F:233
     const float *col = a.hiT + (size_t)e * a.Kp;
     const float *delta = a.din + (size_t)v * a.Kp;
     const float4 *col4 = reinterpret_cast<const float4 *>(col);
     const float4 *d4 = reinterpret_cast<const float4 *>(delta);
+    const int Kp4 = a.Kp >> 2;
     float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 4
-    for (int t = lane; t < (a.Kp >> 2); t += 32) {
+    for (int t = 32 * warp + lane; t < Kp4; t += 32 * LC_WARPS) {
         const float4 h = __ldg(col4 + t);
         const float4 d = __ldg(d4 + t);
         cm[0] = fmaxf(cm[0], __fadd_rn(__fadd_rn(tmp, d.x), h.x));
@@ -216,8 +223,40 @@ __global__ void __launch_bounds__(128) k_flash_last_column(const StepArgs a, int
         cm[2] = fmaxf(cm[2], __fadd_rn(__fadd_rn(tmp, d.z), h.z));
         cm[3] = fmaxf(cm[3], __fadd_rn(__fadd_rn(tmp, d.w), h.w));
     }
-    const Best b = resolve_column(cm, tmp, col, delta, a.LAd, a.K, a.Kp, e, lane);
-    if (lane == 0) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * a.K + e, b.k);
+    const float wtop = warp_max(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
+    if (lane == 0) s_top[warp] = wtop;
+    __syncthreads();
+    float top = s_top[0];
+#pragma unroll
+    for (int w = 1; w < LC_WARPS; ++w) top = fmaxf(top, s_top[w]);
+    Best b{-FLT_MAX, 0x7fffffff};
+    if (top > -FLT_MAX) {
+        const int thr = ford(top) - WINDOW_STEPS;
+        // every lane re-reads its own elements of the chains whose maximum is inside the window
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (ford(cm[c]) < thr) continue;
+            for (int t = 32 * warp + lane; t < Kp4; t += 32 * LC_WARPS) {
+                const int k = 4 * t + c;
+                if (k >= a.K) break;
+                const float pre = __fadd_rn(tmp, __ldg(delta + k));
+                if (ford(__fadd_rn(pre, __ldg(col + k))) >= thr) {
+                    const float x = exact_cand(pre, __ldg(a.LAd + (size_t)k * a.K + e));
+                    if (x > -FLT_MAX) best_take(b, x, k);
+                }
+            }
+        }
+    }
+    b = warp_best(b);
+    if (lane == 0) s_bx[warp] = b.x, s_bk[warp] = b.k;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Best r{s_bx[0], s_bk[0]};
+#pragma unroll
+        for (int w = 1; w < LC_WARPS; ++w) best_take(r, s_bx[w], s_bk[w]);
+        if (!(r.x > -FLT_MAX)) r.k = -1;
+        psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * a.K + e, r.k);
+    }
 }
 
 // ---- end of a full-range pass: Ans[T-1] = first argmax of delta (F:188-195, F:251-258) ----
@@ -409,7 +448,7 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
             }
             if (n_act > n_cont) {
                 a.nact = n_act;
-                k_flash_last_column<<<(n_act - n_cont + 3) / 4, 128, 0, st>>>(a, n_cont, p->d_ans);
+                k_flash_last_column<<<n_act - n_cont, LC_WARPS * 32, 0, st>>>(a, n_cont, p->d_ans);
                 FV_CUDA(cudaGetLastError());
                 ++p->launches;
             }
