@@ -267,6 +267,66 @@ def test_config4_shape_group_engine(fv, oracle_mod, gpu_ctx):
     model.close()
 
 
+@pytest.mark.parametrize("K,quant", [(700, False), (200, True)])
+def test_group_engine_corner_paths(fv, oracle_mod, gpu_ctx, K, quant):
+    """Paths of the group engine the config-4 shape does not reach: a padded K that needs two rounds of
+    column pairs per thread (K=700 -> 768), and a tie-heavy model (quantised probabilities, uniform
+    emissions) where nearly every (column, sequence) pair has several blocks inside the window — more
+    than the per-step list holds, so the in-place column scan runs too.  Group engine == per-step
+    engine on every sequence, == oracle on a sample."""
+    M, T, N, NSEQ = 6, 18, 3, 301
+    A, B, Pi = random_hmm(K, M, 0.2, 300 + K)
+    if quant:
+        A = (np.ceil(A * 4) / 4 * (A > 0)).astype(np.float32)
+        A = (A / np.maximum(A.sum(axis=1, keepdims=True), 1e-9)).astype(np.float32)
+        B = np.ceil(B * M * 2).astype(np.float32)  # two or three distinct emission weights
+        B = (B / B.sum(axis=1, keepdims=True)).astype(np.float32)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    obs = np.random.RandomState(K).randint(0, M, (NSEQ, T)).astype(np.int32)
+    got = {}
+    try:
+        for eng in (fv.ENGINE_PERSISTENT, fv.ENGINE_STEP):
+            plan = fv.Plan(model, T, N, NSEQ, 0, eng)
+            plan.upload(obs)
+            plan.run()
+            got[eng] = plan.download()
+            plan.close()
+        assert np.array_equal(got[fv.ENGINE_PERSISTENT][0], got[fv.ENGINE_STEP][0])
+        assert np.array_equal(_bits(got[fv.ENGINE_PERSISTENT][1]), _bits(got[fv.ENGINE_STEP][1]))
+        for b in (0, 150, NSEQ - 1):
+            want, wscore, _ = om.flash(obs[b], N)
+            assert np.array_equal(got[fv.ENGINE_PERSISTENT][0][b], want), b
+            assert _bits(got[fv.ENGINE_PERSISTENT][1][b]) == _bits(wscore)
+    finally:
+        model.close()
+
+
+def test_sparse_engine_streaming_lists(fv, oracle_mod, gpu_ctx, monkeypatch):
+    """The sparse engine with its edge lists read from L2 every step instead of kept in shared memory
+    (what a model too large for shared memory gets) must decode the same path."""
+    K, M, T = 900, 9, 40
+    A, B, Pi = random_hmm(K, M, 0.1, 77)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    ob = np.random.RandomState(77).randint(0, M, T).astype(np.int32)
+    try:
+        for resident in ("1", "0"):
+            monkeypatch.setenv("FLASHV_SPARSE_RESIDENT", resident)
+            for N in (1, 5, 19):
+                want, wscore, _ = om.flash(ob, N)
+                plan = fv.Plan(model, T, N, 1, 0, fv.ENGINE_SPARSE)
+                plan.upload(ob)
+                plan.run()
+                paths, scores = plan.download()
+                plan.close()
+                assert np.array_equal(paths[0], want), (resident, N)
+                assert _bits(scores[0]) == _bits(wscore)
+    finally:
+        monkeypatch.delenv("FLASHV_SPARSE_RESIDENT")
+        model.close()
+
+
 def test_config4_full_size_batch(fv, oracle_mod, gpu_ctx):
     """BASELINE config 4 at its full size on one GPU: 8192 sequences, K=512, T=1024, at N=32 and at
     the largest segment count the reference accepts (N=511).  The oracle decodes a sample of the
