@@ -156,6 +156,9 @@ constexpr int BS_THREADS = 1024;
 
 struct BsArgs {
     const double *LAd, *LBd, *LPi;
+    const int *csr_cut;       // out-edge lists by source (flash_sparse.cu: sparse_build), or null: dense scoring
+    const uint16_t *csr_i;
+    const double *csr_la;
     const float *LBf;
     int K, Kp, B, T;
     const VecDesc *vecs;
@@ -310,8 +313,9 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
     const int32_t *ob = a.ob + (size_t)vd.seq * T;
     int32_t *ans = a.ans + (size_t)vd.seq * T;
     const bool full = (vd.flags & VEC_FULL_RANGE) != 0;
-    const int per = (K + CS - 1) / CS;  // states per CTA
-    const int s_lo = rank * per, s_hi = min(K, s_lo + per);
+    // states per CTA: 8/CS consecutive eighths of the state range (the eighths are where the out-edge lists are cut)
+    const int per8 = (K + 7) / 8, q_lo = rank * (8 / CS), q_hi = q_lo + 8 / CS;
+    const int s_lo = min(K, q_lo * per8), s_hi = min(K, q_hi * per8);
     float *peer_score[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) peer_score[r] = r < CS ? cluster.map_shared_rank(sscore, r) : sscore;
@@ -342,6 +346,93 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
         const long long c0 = clock64();
         const int o = ob[j];
         const bool keep = j >= vd.mid + 1;  // S:448: payload latches at j == mid+1
+        if (a.csr_cut) {
+            // ---- scoring over the out-edges of the beam states (S:437-446 restricted to the candidates that
+            // can win: an entry with A[s][i] == 0 gives -inf and never passes the strict '>').  Warp per
+            // beam entry, lanes over the part of its out-edge list that falls into this CTA's states.
+            // Pass 1: maximum per destination (shared-memory atomicMax on a monotone key).  Pass 2: the
+            // same edges again — the ones attaining the maximum leave the smallest slot index and their
+            // number (two or more = the reference's choice depends on the heap's slot order).
+            unsigned *skey = reinterpret_cast<unsigned *>(bs + 1);  // [per8 * 8 / CS] each
+            int *sslot = reinterpret_cast<int *>(skey + (s_hi - s_lo));
+            int *scnt = sslot + (s_hi - s_lo);
+            const int nloc = s_hi - s_lo;
+            const unsigned KEY_DEAD = score_key(-FLT_MAX);
+            for (int t = tid; t < nloc; t += nthr) skey[t] = KEY_DEAD, sslot[t] = 0x7fffffff, scnt[t] = 0;
+            __syncthreads();
+            const float *tmp_row = a.LBf + (size_t)o * a.Kp;  // S:439
+            const int warp = tid >> 5, nwarp = nthr >> 5;
+            // A warp takes UE beam entries at a time so that their list bounds, then their edges, are
+            // requested together: the walk is a chain of dependent L2 reads (bounds -> edge -> emission
+            // term), paid once per UE entries instead of once per entry.  Pass 2 re-reads the same
+            // ~70 KB per CTA from L1.
+            auto walk = [&](auto ue) {
+            constexpr int UE = decltype(ue)::value;
+#pragma unroll 1
+            for (int pass2 = 0; pass2 < 2; ++pass2) {
+                for (int c0 = warp; c0 < B; c0 += nwarp * UE) {  // entries c0, c0 + nwarp, ...: small beams still use every warp
+                    HeapNode h[UE];
+                    int e0[UE], e1[UE], longest = 0;
+#pragma unroll
+                    for (int u = 0; u < UE; ++u) {
+                        h[u] = beam[min(c0 + u * nwarp, B - 1)];
+                        e0[u] = __ldg(a.csr_cut + (size_t)h[u].s * 9 + q_lo);
+                        e1[u] = c0 + u * nwarp < B ? __ldg(a.csr_cut + (size_t)h[u].s * 9 + q_hi) : 0;  // a missing entry has no edges
+                    }
+#pragma unroll
+                    for (int u = 0; u < UE; ++u) longest = max(longest, e1[u] - e0[u]);
+                    for (int off = lane; off < longest; off += 32) {
+                        int i[UE];
+                        double la[UE];
+                        float tmpv[UE];
+                        bool on[UE];
+#pragma unroll
+                        for (int u = 0; u < UE; ++u) {
+                            on[u] = e0[u] + off < e1[u];
+                            i[u] = on[u] ? (int)__ldg(a.csr_i + e0[u] + off) : s_lo;
+                            la[u] = on[u] ? __ldg(a.csr_la + e0[u] + off) : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < UE; ++u) tmpv[u] = __ldg(tmp_row + i[u]);
+#pragma unroll
+                        for (int u = 0; u < UE; ++u) {
+                            const float x = exact_cand(__fadd_rn(tmpv[u], h[u].v), la[u]);
+                            if (!on[u] || !(x > -FLT_MAX)) continue;
+                            const unsigned key = score_key(x);
+                            if (pass2 == 0) {
+                                atomicMax(&skey[i[u] - s_lo], key);
+                            } else if (key == skey[i[u] - s_lo]) {
+                                atomicMin(&sslot[i[u] - s_lo], c0 + u * nwarp);
+                                atomicAdd(&scnt[i[u] - s_lo], 1);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            };
+            if (B > nwarp)
+                walk(std::integral_constant<int, 4>());
+            else
+                walk(std::integral_constant<int, 1>());  // small beams: one entry per warp, nothing to batch
+            for (int t = tid; t < nloc; t += nthr) {
+                const int i = s_lo + t;
+                float best = -FLT_MAX;
+                int arg = -1;
+                if (skey[t] != KEY_DEAD) {
+                    const int ob32 = (int)(skey[t] ^ 0x80000000u);  // inverse of score_key: ordinal -> float bits
+                    best = __int_as_float(ob32 >= 0 ? ob32 : (int)((unsigned)(-ob32) | 0x80000000u));
+                    arg = beam[sslot[t]].s;
+                }
+                const bool tie = scnt[t] > 1;
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r < CS) peer_score[r][i] = best;
+                // with the true heap in beam[] (slot order) the smallest slot IS the reference's choice
+                if (keep) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + i,
+                                    arg >= 0 && tie && !have_heap ? arg | a.flagbit : arg);
+            }
+        } else {
         // (the loop bound is rounded up to whole pairs: both threads of a pair reach the shuffles)
         for (int li = tid >> 1; li < ((s_hi - s_lo + 15) & ~15); li += nthr >> 1) {
             const int i = s_lo + li;
@@ -391,6 +482,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
                 if (keep) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + i,
                                     arg >= 0 && tie && !have_heap ? arg | a.flagbit : arg);
             }
+        }
         }
         cluster.sync();  // all scores of step j are in every CTA's vector
         const long long c1 = clock64();
@@ -444,7 +536,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
 
 static size_t bs_smem_bytes(int Kp, int B)
 {
-    return (size_t)Kp * 4 + (size_t)(((B + 1) & ~1) + 2 * B + 4) * sizeof(HeapNode) + sizeof(BeamScratch) + 16;
+    // + the sparse scoring's per-destination key / slot / count arrays (at most all K states in one CTA)
+    return (size_t)Kp * 4 + (size_t)(((B + 1) & ~1) + 2 * B + 4) * sizeof(HeapNode) + sizeof(BeamScratch) + (size_t)3 * Kp * 4 + 16;
 }
 
 int bs_run_pass(flashv_plan *p, const Pass &pass)
@@ -453,6 +546,8 @@ int bs_run_pass(flashv_plan *p, const Pass &pass)
     flashv_ctx *ctx = m->ctx;
     BsArgs a;
     a.LAd = m->LAd, a.LBd = m->LBd, a.LPi = m->LPi, a.LBf = m->LBf;
+    const bool dense_scoring = getenv("FLASHV_BS_DENSE") && atoi(getenv("FLASHV_BS_DENSE")) != 0;  // tests: force the K x B table reads
+    a.csr_cut = dense_scoring ? nullptr : m->csr_cut, a.csr_i = m->csr_i, a.csr_la = m->csr_la;
     a.K = m->K, a.Kp = m->Kp, a.B = p->B, a.T = p->T;
     a.vecs = p->d_vecs + pass.vec_offset, a.nvec = pass.nvec;
     a.ob = p->d_ob, a.ans = p->d_ans, a.score = p->d_score;

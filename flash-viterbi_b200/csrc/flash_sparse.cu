@@ -298,6 +298,33 @@ int sparse_build(flashv_model *m, const double *hLA)
     }
     m->csc_max_cta_nnz = worst;
     m->bytes += ((size_t)K + 1) * sizeof(int) + nnz * (sizeof(uint16_t) + sizeof(double));
+
+    // The same edges by SOURCE for FLASH-BS (a step only looks at the out-edges of the B beam states),
+    // with every row cut at the 8 destination-range boundaries q*ceil(K/8) a cluster's CTAs own.
+    {
+        const int per8 = (K + 7) / 8;
+        std::vector<int> cut((size_t)K * 9);
+        std::vector<uint16_t> ri(nnz);
+        std::vector<double> rla(nnz);
+        size_t e = 0;
+        for (int k = 0; k < K; ++k) {
+            const double *row = hLA + (size_t)k * K;
+            int q = 0;
+            for (int i = 0; i < K; ++i) {
+                while (q < 9 && i >= q * per8) cut[(size_t)k * 9 + q++] = (int)e;
+                if (row[i] > -INFINITY) ri[e] = (uint16_t)i, rla[e] = row[i], ++e;
+            }
+            while (q < 9) cut[(size_t)k * 9 + q++] = (int)e;
+        }
+        FV_CUDA(cudaMalloc(&m->csr_cut, cut.size() * sizeof(int)));
+        FV_CUDA(cudaMalloc(&m->csr_i, nnz * sizeof(uint16_t)));
+        FV_CUDA(cudaMalloc(&m->csr_la, nnz * sizeof(double)));
+        FV_CUDA(cudaMemcpyAsync(m->csr_cut, cut.data(), cut.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        FV_CUDA(cudaMemcpyAsync(m->csr_i, ri.data(), nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        FV_CUDA(cudaMemcpyAsync(m->csr_la, rla.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        FV_CUDA(cudaStreamSynchronize(ctx->stream));
+        m->bytes += cut.size() * sizeof(int) + nnz * (sizeof(uint16_t) + sizeof(double));
+    }
     return FLASHV_OK;
 }
 

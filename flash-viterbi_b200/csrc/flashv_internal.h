@@ -91,6 +91,9 @@ struct flashv_model {
     uint16_t *csc_k = nullptr;
     double *csc_la = nullptr;
     long long csc_nnz = 0;
+    int *csr_cut = nullptr;       // out-edge lists for FLASH-BS (bs_kernels.cu): row s, cut q = first entry with destination >= q*ceil(K/8); [K][9]
+    uint16_t *csr_i = nullptr;    // [nnz] destination state, ascending within a row
+    double *csr_la = nullptr;     // [nnz] log A[s][i]
     int csc_max_cta_nnz = 0;
     float *hiS = nullptr;     // [Kp][Kp] the same, source-major (hiS[k][i]), for the group engine; only when Kp <= 1536
     int tile_G = 0;           // grid the tiling was built for (min(#SM, K))

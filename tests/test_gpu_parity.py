@@ -191,14 +191,18 @@ def test_flash_bs_select_path_equals_replay_path(fv, oracle_mod, gpu_ctx, monkey
         for N, Bw in [(1, 8), (4, 16), (5, 3), (1, K)]:
             ob = rng.randint(0, M, T).astype(np.int32)
             want, wscore, _ = om.flash_bs(ob, N, Bw)
-            for mode, cs in (("0", "1"), ("1", "1"), ("0", "8"), ("0", "2"), ("1", "4")):
+            # (replay every step?, CTAs per vector, K x B table reads instead of the out-edge lists?)
+            for mode, cs, dense in (("0", "1", "0"), ("1", "1", "0"), ("0", "8", "0"), ("0", "2", "1"), ("1", "4", "1"),
+                                    ("0", "4", "0"), ("0", "8", "1")):
                 monkeypatch.setenv("FLASHV_BS_REPLAY", mode)
-                monkeypatch.setenv("FLASHV_BS_CLUSTER", cs)  # CTAs per vector (scores cross SMs through DSMEM)
+                monkeypatch.setenv("FLASHV_BS_CLUSTER", cs)  # scores cross SMs through DSMEM
+                monkeypatch.setenv("FLASHV_BS_DENSE", dense)
                 got, score, _ = model.bs_decode(ob, N, Bw)
-                assert np.array_equal(got, want), (K, N, Bw, mode, cs)
-                assert _bits(score) == _bits(wscore), (K, N, Bw, mode, cs)
+                assert np.array_equal(got, want), (K, N, Bw, mode, cs, dense)
+                assert _bits(score) == _bits(wscore), (K, N, Bw, mode, cs, dense)
         monkeypatch.delenv("FLASHV_BS_REPLAY")
         monkeypatch.delenv("FLASHV_BS_CLUSTER")
+        monkeypatch.delenv("FLASHV_BS_DENSE")
         model.close()
 
 
