@@ -1,12 +1,16 @@
 // bs_kernels.cu — FLASH-BS passes on the device.
 //
-// One CTA owns one trellis vector (a sequence's first pass or one task) for all of its steps, so
-// a pass needs no grid-wide synchronisation: per step the CTA's threads score every destination
-// state against the B beam entries in heap-array order (S:437-446, exact double chain), then
-// warp 0 rebuilds the beam by replaying the reference's min-heap insertions over the K scores
-// (S:167-211) — the array layout of the heap is observable (next step scans slots in order with
-// strict '>', the end scan of S:376-381 looks at slot 1 and slots B/2+2..B only), so the set of
-// the top-B alone is not enough.
+// One thread-block cluster owns one trellis vector (a sequence's first pass or one task) for all of
+// its steps, so a pass needs no grid-wide synchronisation.  Per step
+//   1. the cluster scores every destination state against the B beam entries with the exact double
+//      chain (S:437-446) — over the out-edge lists of the beam states when the model has them
+//      (entries with A[s][i] == 0 give -inf and never win), else over the K x B table reads — and
+//      all-gathers the scores into every CTA's shared memory;
+//   2. every CTA builds the next beam with a radix select; the reference's min-heap insertions
+//      (S:167-211) are replayed only where the heap's array layout is observable: ties at the beam's
+//      minimum, the end scan of S:376-381 (slot 1 and slots B/2+2..B), and — at backtrack time — a
+//      visited backpointer whose maximum was attained by two beam states (the next step scans the
+//      slots in order with a strict '>').  See build_beam() for why the set alone suffices otherwise.
 //
 // The per-entry payload T3_State (S:55) is not carried in the heap: every step's predecessor
 // state psi_j[i] goes to the backpointer store and the payload is recovered by walking it back
