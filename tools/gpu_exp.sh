@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for n in 32 511; do
-timeout 600 python tools/profile_target.py --K 512 --T 1024 --batch 8192 --segments $n --iters 2
-done
+P="python tools/profile_target.py --engine sparse --segments 127 --iters 2"
+$P > gpurun_out/plain_sparse.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_flash_sparse_pass -s 1 -c 1 -f -o gpurun_out/prof_sparse $P > gpurun_out/ncu_sparse.log 2>&1
+cat gpurun_out/plain_sparse.log; tail -2 gpurun_out/ncu_sparse.log
