@@ -271,10 +271,10 @@ def test_config4_shape_group_engine(fv, oracle_mod, gpu_ctx):
     model.close()
 
 
-@pytest.mark.parametrize("K,quant", [(700, False), (200, True)])
+@pytest.mark.parametrize("K,quant", [(700, False), (200, True), (37, False)])
 def test_group_engine_corner_paths(fv, oracle_mod, gpu_ctx, K, quant):
     """Paths of the group engine the config-4 shape does not reach: a padded K that needs two rounds of
-    column pairs per thread (K=700 -> 768), and a tie-heavy model (quantised probabilities, uniform
+    column pairs per thread (K=700 -> 768), an odd K whose last column pair is half padding (K=37), and a tie-heavy model (quantised probabilities, uniform
     emissions) where nearly every (column, sequence) pair has several blocks inside the window — more
     than the per-step list holds, so the in-place column scan runs too.  Group engine == per-step
     engine on every sequence, == oracle on a sample."""
