@@ -1,3 +1,7 @@
 #!/bin/bash
+# scratch script for the experiment at hand: here, the whole GPU suite and smoke() against HEAD
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x --timeout 300 -p no:cacheprovider -k "corner or large_batch" 2>&1 | tail -4
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
