@@ -62,7 +62,9 @@ __device__ __forceinline__ unsigned long long sp_now_ns()
 // alternatives, both slower than polling the words themselves (0.84 ms per 255-step pass): polling
 // one sentinel word per producer CTA first and reading the vector afterwards (1.03 ms: one more
 // dependent round trip), and a separate array of per-CTA flags (2.01 ms: 148 CTAs spinning on the
-// same five cache lines serialise in one L2 slice).
+// same five cache lines serialise in one L2 slice).  Dropping the end-of-step block barrier (ping-pong
+// delta buffers) is also slower, 2.2 ms: warps that finish early start polling at once and their
+// traffic slows the CTAs that still have to publish — the barrier is the back-off.
 __device__ __forceinline__ void sp_delta_load(const SparseArgs &a, int s, float *sdelta, int tid)
 {
     if (s == 1) {
