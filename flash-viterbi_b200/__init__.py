@@ -36,8 +36,12 @@ ABI_SYMBOLS = [
     "flashv_decode", "flashv_bs_decode", "flashv_decode_batch", "flashv_bs_decode_batch",
     "flashv_plan_create", "flashv_plan_destroy", "flashv_plan_upload", "flashv_plan_run",
     "flashv_plan_download", "flashv_plan_report",
-    "flashv_plan_shard_init", "flashv_plan_shard_buffers", "flashv_plan_shard_ipc_handles",
+    "flashv_plan_shard_init", "flashv_plan_shard_buffers", "flashv_plan_shard_ipc_handle",
     "flashv_plan_shard_set_peer", "flashv_plan_shard_open_peer",
+    "flashv_model_create_rows", "flashv_model_rows_handle", "flashv_model_pull_rows", "flashv_model_pull_rows_from",
+    "flashv_model_finish", "flashv_shard_count", "flashv_decode_batch_shard",
+    "flashv_mgpu_create", "flashv_mgpu_destroy", "flashv_mgpu_world", "flashv_mgpu_ctx", "flashv_mgpu_model",
+    "flashv_mgpu_model_create", "flashv_mgpu_decode_batch", "flashv_mgpu_decode",
     "flashv_read_floats_cached", "flashv_trellis_init", "flashv_trellis_step", "flashv_bs_score_step", "flashv_bs_heap_replay",
     "flashv_task_list", "flashv_executed_steps", "flashv_memory_bytes", "flashv_bs_memory_bytes",
 ]
@@ -117,10 +121,28 @@ def lib():
     L.flashv_plan_download.argtypes = [vp, ip, fp]
     L.flashv_plan_report.argtypes = [vp, rp]
     L.flashv_plan_shard_init.argtypes = [vp, C.c_int, C.c_int]
-    L.flashv_plan_shard_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
-    L.flashv_plan_shard_ipc_handles.argtypes = [vp, vp]
-    L.flashv_plan_shard_set_peer.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.flashv_plan_shard_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.flashv_plan_shard_ipc_handle.argtypes = [vp, vp]
+    L.flashv_plan_shard_set_peer.argtypes = [vp, C.c_int, C.c_int, vp]
     L.flashv_plan_shard_open_peer.argtypes = [vp, C.c_int, vp]
+    L.flashv_model_create_rows.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.flashv_model_rows_handle.argtypes = [vp, vp]
+    L.flashv_model_pull_rows.argtypes = [vp, C.c_int, vp]
+    L.flashv_model_pull_rows_from.argtypes = [vp, C.c_int, vp]
+    L.flashv_model_finish.argtypes = [vp]
+    L.flashv_shard_count.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.flashv_decode_batch_shard.argtypes = [vp, ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, fp, rp]
+    L.flashv_mgpu_create.argtypes = [C.c_int, ip, C.POINTER(vp)]
+    L.flashv_mgpu_destroy.argtypes = [vp]
+    L.flashv_mgpu_destroy.restype = None
+    L.flashv_mgpu_world.argtypes = [vp]
+    L.flashv_mgpu_ctx.argtypes = [vp, C.c_int]
+    L.flashv_mgpu_ctx.restype = vp
+    L.flashv_mgpu_model.argtypes = [vp, C.c_int]
+    L.flashv_mgpu_model.restype = vp
+    L.flashv_mgpu_model_create.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp]
+    L.flashv_mgpu_decode_batch.argtypes = [vp, ip, C.c_int, C.c_int, C.c_int, ip, fp, rp]
+    L.flashv_mgpu_decode.argtypes = [vp, ip, C.c_int, C.c_int, ip, fp, rp]
     L.flashv_trellis_init.argtypes = [vp, C.c_int, C.c_int, fp]
     L.flashv_trellis_step.argtypes = [vp, fp, C.c_int, fp, ip, C.c_int]
     L.flashv_bs_score_step.argtypes = [vp, fp, ip, C.c_int, C.c_int, fp, ip]
@@ -254,9 +276,51 @@ class Model:
         self._h = C.c_void_p()
         _check(lib().flashv_model_create(ctx._h, K, M, _f(A), _f(B), _f(Pi), C.byref(self._h)))
 
+    @classmethod
+    def create_rows(cls, ctx: "Context", A, B, Pi, rank, world):
+        """Model creation shared by the ranks of a box: this rank's rows of host logarithms only; fetch the
+        rest with pull_rows() after a barrier, then finish() after another (include/flashv.h).  A may be a
+        read-only mapping shared by the ranks (only this rank's rows are read)."""
+        self = cls.__new__(cls)
+        A = np.asarray(A)
+        assert A.dtype == np.float32 and A.flags.c_contiguous
+        B = np.ascontiguousarray(B, np.float32)
+        Pi = np.ascontiguousarray(Pi, np.float32)
+        K, M = B.shape
+        self.ctx, self.K, self.M = ctx, K, M
+        self._h = C.c_void_p()
+        _check(lib().flashv_model_create_rows(ctx._h, K, M, _f(A), _f(B), _f(Pi), rank, world, C.byref(self._h)))
+        return self
+
+    def rows_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(lib().flashv_model_rows_handle(self._h, buf))
+        return buf.raw
+
+    def pull_rows(self, peer_rank, handle: bytes):
+        _check(lib().flashv_model_pull_rows(self._h, peer_rank, C.create_string_buffer(handle, 64)))
+
+    def pull_rows_from(self, peer_rank, peer: "Model"):
+        _check(lib().flashv_model_pull_rows_from(self._h, peer_rank, peer._h))
+
+    def finish(self):
+        _check(lib().flashv_model_finish(self._h))
+
     @property
     def prep_ms(self):
         return lib().flashv_model_prep_ms(self._h)
+
+    def decode_batch_shard(self, obs, N, rank, world, paths=None, scores=None):
+        """This rank's share (rows rank, rank+world, ...) of obs[total][T], left in place in paths/scores."""
+        obs = np.ascontiguousarray(obs, np.int32)
+        total, T = obs.shape
+        if paths is None:
+            paths = np.full((total, T), -2, np.int32)
+        if scores is None:
+            scores = np.zeros(total, np.float32)
+        rep = Report()
+        _check(lib().flashv_decode_batch_shard(self._h, _i(obs), total, T, N, rank, world, _i(paths), _f(scores), C.byref(rep)))
+        return paths, scores, rep
 
     def decode(self, ob, N):
         """calc() of FLASH (F:338-368): (path[T], score, report)."""
@@ -354,20 +418,21 @@ class Plan:
         _check(lib().flashv_plan_shard_init(self._h, rank, world))
 
     def shard_buffers(self):
-        d, s = C.c_void_p(), C.c_void_p()
-        _check(lib().flashv_plan_shard_buffers(self._h, C.byref(d), C.byref(s)))
-        return d.value, s.value
+        """(base address, bytes) of the region this plan's peers store into."""
+        d, n = C.c_void_p(), C.c_size_t()
+        _check(lib().flashv_plan_shard_buffers(self._h, C.byref(d), C.byref(n)))
+        return d.value, n.value
 
-    def shard_ipc_handles(self) -> bytes:
-        buf = C.create_string_buffer(128)
-        _check(lib().flashv_plan_shard_ipc_handles(self._h, buf))
+    def shard_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(lib().flashv_plan_shard_ipc_handle(self._h, buf))
         return buf.raw
 
-    def shard_set_peer(self, peer_rank, peer_device, delta_ptr, psi_ptr):
-        _check(lib().flashv_plan_shard_set_peer(self._h, peer_rank, peer_device, C.c_void_p(delta_ptr), C.c_void_p(psi_ptr)))
+    def shard_set_peer(self, peer_rank, peer_device, region_ptr):
+        _check(lib().flashv_plan_shard_set_peer(self._h, peer_rank, peer_device, C.c_void_p(region_ptr)))
 
-    def shard_open_peer(self, peer_rank, handles: bytes):
-        buf = C.create_string_buffer(handles, 128)
+    def shard_open_peer(self, peer_rank, handle: bytes):
+        buf = C.create_string_buffer(handle, 64)
         _check(lib().flashv_plan_shard_open_peer(self._h, peer_rank, buf))
 
     def report(self):
@@ -378,6 +443,59 @@ class Plan:
     def close(self):
         if self._h:
             lib().flashv_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def shard_count(total, rank, world):
+    return int(lib().flashv_shard_count(total, rank, world))
+
+
+class MultiGpu:
+    """Every GPU of the box from one host process (flashv_mgpu_*): replicated model built once with the
+    host logarithms split over the devices' threads, batches sharded b mod G, single sequences state-sharded."""
+
+    def __init__(self, ndev, devices=None):
+        self._h = C.c_void_p()
+        dv = np.ascontiguousarray(devices, np.int32) if devices is not None else None
+        _check(lib().flashv_mgpu_create(ndev, _i(dv) if dv is not None else None, C.byref(self._h)))
+        self.world = int(lib().flashv_mgpu_world(self._h))
+        self.K = self.M = 0
+
+    def model_create(self, A, B, Pi):
+        A = np.ascontiguousarray(A, np.float32)
+        B = np.ascontiguousarray(B, np.float32)
+        Pi = np.ascontiguousarray(Pi, np.float32)
+        self.K, self.M = B.shape
+        _check(lib().flashv_mgpu_model_create(self._h, self.K, self.M, _f(A), _f(B), _f(Pi)))
+
+    def prep_ms(self, rank=0):
+        return lib().flashv_model_prep_ms(lib().flashv_mgpu_model(self._h, rank))
+
+    def decode_batch(self, obs, N):
+        obs = np.ascontiguousarray(obs, np.int32)
+        batch, T = obs.shape
+        paths = np.empty((batch, T), np.int32)
+        scores = np.empty(batch, np.float32)
+        rep = Report()
+        _check(lib().flashv_mgpu_decode_batch(self._h, _i(obs), batch, T, N, _i(paths), _f(scores), C.byref(rep)))
+        return paths, scores, rep
+
+    def decode(self, ob, N):
+        ob = np.ascontiguousarray(ob, np.int32)
+        path = np.empty(ob.shape[0], np.int32)
+        score, rep = C.c_float(), Report()
+        _check(lib().flashv_mgpu_decode(self._h, _i(ob), ob.shape[0], N, _i(path), C.byref(score), C.byref(rep)))
+        return path, np.float32(score.value), rep
+
+    def close(self):
+        if self._h:
+            lib().flashv_mgpu_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -76,6 +76,7 @@ extern "C" int flashv_ctx_create(int device, void *stream, flashv_ctx **out)
         c->own_stream = true;
     }
     for (auto &ev : c->ev) FV_CUDA(cudaEventCreate(&ev));
+    for (auto &ev : c->ev_prep) FV_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     *out = c;
     return FLASHV_OK;
 }
@@ -87,7 +88,11 @@ extern "C" void flashv_ctx_destroy(flashv_ctx *c)
     cudaStreamSynchronize(c->stream);
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->ev_prep)
+        if (ev) cudaEventDestroy(ev);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (auto &b : c->h_prep)
+        if (b) cudaFreeHost(b);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -112,11 +117,11 @@ static int stage_reserve(flashv_ctx *c, size_t bytes)
 }
 
 // ---- model ---------------------------------------------------------------------------------
-extern "C" int flashv_model_create(flashv_ctx *ctx, int K, int M, const float *A, const float *B, const float *Pi,
-                                   flashv_model **out)
+static int model_new(flashv_ctx *ctx, int K, int M, const float *A, const float *B, const float *Pi, flashv_model **out,
+                     const char *who)
 {
     if (!ctx || !A || !B || !Pi || !out || K < 1 || M < 1) {
-        set_error("flashv_model_create: bad argument");
+        set_error("%s: bad argument", who);
         return FLASHV_ERR_ARG;
     }
     *out = nullptr;
@@ -124,13 +129,124 @@ extern "C" int flashv_model_create(flashv_ctx *ctx, int K, int M, const float *A
     flashv_model *m = new flashv_model();
     m->ctx = ctx, m->K = K, m->M = M;
     m->Kp = (K + 127) / 128 * 128;
-    int rc = tables_build(m, A, B, Pi);
+    int rc = tables_alloc(m);
     if (rc != FLASHV_OK) {
         flashv_model_destroy(m);
         return rc;
     }
     *out = m;
     return FLASHV_OK;
+}
+
+extern "C" int flashv_model_create(flashv_ctx *ctx, int K, int M, const float *A, const float *B, const float *Pi,
+                                   flashv_model **out)
+{
+    flashv_model *m = nullptr;
+    int rc = model_new(ctx, K, M, A, B, Pi, &m, "flashv_model_create");
+    if (rc != FLASHV_OK) return rc;
+    rc = tables_logs(m, A, B, Pi, 0, K, 1);
+    if (rc == FLASHV_OK) rc = tables_layouts(m);
+    if (rc != FLASHV_OK) {
+        flashv_model_destroy(m);
+        *out = nullptr;
+        return rc;
+    }
+    *out = m;
+    return FLASHV_OK;
+}
+
+// A model created in parts (include/flashv.h "model creation shared by the ranks of a box"): the host
+// logarithms are what model creation costs (one libm call per table entry, F:170), so `world` ranks
+// each compute K/world rows and fetch the rest from the peers' device tables over NVLink.
+extern "C" int flashv_model_create_rows(flashv_ctx *ctx, int K, int M, const float *A, const float *B, const float *Pi,
+                                        int rank, int world, flashv_model **out)
+{
+    if (world < 1 || rank < 0 || rank >= world) {
+        set_error("flashv_model_create_rows: rank %d of %d", rank, world);
+        return FLASHV_ERR_ARG;
+    }
+    flashv_model *m = nullptr;
+    int rc = model_new(ctx, K, M, A, B, Pi, &m, "flashv_model_create_rows");
+    if (rc != FLASHV_OK) return rc;
+    const int lo = (int)((long long)rank * K / world), hi = (int)((long long)(rank + 1) * K / world);
+    rc = tables_logs(m, A, B, Pi, lo, hi, world);
+    if (rc != FLASHV_OK) {
+        flashv_model_destroy(m);
+        *out = nullptr;
+        return rc;
+    }
+    m->part_rank = rank, m->part_world = world;
+    *out = m;
+    return FLASHV_OK;
+}
+
+extern "C" int flashv_model_rows_handle(flashv_model *m, void *out64)
+{
+    if (!m || !out64) {
+        set_error("flashv_model_rows_handle: bad argument");
+        return FLASHV_ERR_ARG;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "one handle fills 64 bytes");
+    FV_CUDA(cudaSetDevice(m->ctx->device));
+    cudaIpcMemHandle_t h;
+    FV_CUDA(cudaIpcGetMemHandle(&h, m->LAd));
+    memcpy(out64, &h, sizeof(h));
+    return FLASHV_OK;
+}
+
+static int pull_rows(flashv_model *m, int peer_rank, const double *peer_LAd)
+{
+    const int K = m->K;
+    const int lo = (int)((long long)peer_rank * K / m->part_world), hi = (int)((long long)(peer_rank + 1) * K / m->part_world);
+    if (hi > lo)
+        FV_CUDA(cudaMemcpyAsync(m->LAd + (size_t)lo * K, peer_LAd + (size_t)lo * K, (size_t)(hi - lo) * K * sizeof(double),
+                                cudaMemcpyDefault, m->ctx->stream));
+    return FLASHV_OK;
+}
+
+extern "C" int flashv_model_pull_rows(flashv_model *m, int peer_rank, const void *handle64)
+{
+    if (!m || !handle64 || m->ready || peer_rank < 0 || peer_rank >= m->part_world || peer_rank == m->part_rank) {
+        set_error("flashv_model_pull_rows: bad argument or model already finished");
+        return FLASHV_ERR_ARG;
+    }
+    FV_CUDA(cudaSetDevice(m->ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void *peer = nullptr;
+    FV_CUDA(cudaIpcOpenMemHandle(&peer, h, cudaIpcMemLazyEnablePeerAccess));
+    int rc = pull_rows(m, peer_rank, reinterpret_cast<const double *>(peer));
+    cudaError_t e = cudaStreamSynchronize(m->ctx->stream);
+    cudaIpcCloseMemHandle(peer);
+    if (rc == FLASHV_OK && e != cudaSuccess) rc = cuda_fail(e, "pull rows", __FILE__, __LINE__);
+    return rc;
+}
+
+extern "C" int flashv_model_pull_rows_from(flashv_model *m, int peer_rank, const flashv_model *peer)
+{
+    if (!m || !peer || m->ready || peer_rank < 0 || peer_rank >= m->part_world || peer->K != m->K) {
+        set_error("flashv_model_pull_rows_from: bad argument or model already finished");
+        return FLASHV_ERR_ARG;
+    }
+    FV_CUDA(cudaSetDevice(m->ctx->device));
+    if (peer->ctx->device != m->ctx->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->ctx->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+        cudaGetLastError();
+    }
+    int rc = pull_rows(m, peer_rank, peer->LAd);
+    if (rc == FLASHV_OK) FV_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return rc;
+}
+
+extern "C" int flashv_model_finish(flashv_model *m)
+{
+    if (!m || m->ready) {
+        set_error("flashv_model_finish: no model, or already finished");
+        return FLASHV_ERR_ARG;
+    }
+    FV_CUDA(cudaSetDevice(m->ctx->device));
+    return tables_layouts(m);
 }
 
 extern "C" void flashv_model_destroy(flashv_model *m)
@@ -186,6 +302,10 @@ extern "C" int flashv_plan_create(flashv_model *m, int T, int N, int batch, int 
         set_error("flashv_plan_create: BeamSearchWidth %d > K %d (the reference scans stale slots there)", B, m->K);
         return FLASHV_ERR_ARG;
     }
+    if (!m->ready) {
+        set_error("flashv_plan_create: the model was created in parts and flashv_model_finish has not run");
+        return FLASHV_ERR_STATE;
+    }
     flashv_ctx *ctx = m->ctx;
     FV_CUDA(cudaSetDevice(ctx->device));
     flashv_plan *p = new flashv_plan();
@@ -195,7 +315,22 @@ extern "C" int flashv_plan_create(flashv_model *m, int T, int N, int batch, int 
         set_error("flashv_plan_create: unsupported (T=%d, N=%d): need T >= 2, N >= 1 and not T == 2N with N > 2", T, N);
         return FLASHV_ERR_ARG;
     }
-    if (engine == FLASHV_ENGINE_AUTO) engine = ctx->coop ? FLASHV_ENGINE_PERSISTENT : FLASHV_ENGINE_STEP;
+    // Engine feasibility is decided here, not at run time: the persistent kernel needs the delta vector
+    // plus two ring stages in one CTA's shared memory (K up to ~42 k), the per-step kernels the delta
+    // vector alone (K <= 56,320, the largest K a FLASH plan accepts; include/flashv.h).
+    const bool persist_ok = persistent_engine_fits(ctx, m->Kp);
+    if (B == 0 && m->Kp > STEP_MAX_KP) {
+        delete p;
+        set_error("flashv_plan_create: K=%d is beyond the largest supported K (%d): one delta vector must fit shared memory", m->K, STEP_MAX_KP);
+        return FLASHV_ERR_ARG;
+    }
+    if (engine == FLASHV_ENGINE_AUTO) engine = persist_ok ? FLASHV_ENGINE_PERSISTENT : FLASHV_ENGINE_STEP;
+    if (engine == FLASHV_ENGINE_PERSISTENT && B == 0 && !persist_ok) {
+        delete p;
+        set_error("flashv_plan_create: the persistent engine does not fit K=%d on this device (no cooperative launch, or delta + two ring "
+                  "stages exceed %d bytes of shared memory); use FLASHV_ENGINE_AUTO or FLASHV_ENGINE_STEP", m->K, ctx->smem_optin);
+        return FLASHV_ERR_ARG;
+    }
     if (engine == FLASHV_ENGINE_SPARSE && (!sparse_engine_available(m) || !ctx->coop || B > 0)) {
         delete p;
         set_error("flashv_plan_create: the sparse engine needs a FLASH plan, a cooperative-launch device and a model whose "
@@ -275,14 +410,50 @@ extern "C" void flashv_plan_destroy(flashv_plan *p)
     cudaSetDevice(p->model->ctx->device);
     cudaStreamSynchronize(p->model->ctx->stream);
     for (int r = 0; r < 8; ++r)
-        if (p->peer_ipc[r]) cudaIpcCloseMemHandle(p->peer_delta[r]), cudaIpcCloseMemHandle(p->peer_psi[r]);
-    cudaFree(p->hiC_shard);
+        if (p->peer_ipc[r]) cudaIpcCloseMemHandle(p->peer_region[r]);
+    cudaFree(p->hiC_shard), cudaFree(p->shard_region), cudaFree(p->d_lvl_mid);
     cudaFree(p->d_ob), cudaFree(p->d_ans), cudaFree(p->d_score), cudaFree(p->d_delta), cudaFree(p->d_psi);
     cudaFree(p->d_vecs), cudaFree(p->d_ismid), cudaFree(p->d_endstate), cudaFree(p->d_sync), cudaFree(p->d_bs_score);
     delete p;
 }
 
 // ---- state sharding across GPUs ------------------------------------------------------
+// Rebuild the level passes of a sharded plan so that this rank runs every world-th task of a level
+// (tasks are sorted longest first, so round-robin balances the steps), and record which Ans entries
+// every level produces: they are exchanged after the level (shard_ans_exchange).
+static int shard_spread_levels(flashv_plan *p)
+{
+    const int first = p->sched.first_pass ? 1 : 0;
+    std::vector<VecDesc> all;
+    std::vector<Pass> old;
+    old.swap(p->passes);
+    std::vector<int32_t> mids;
+    p->lvl_off.clear(), p->lvl_cnt.clear();
+    size_t li = 0;
+    if (first) {
+        std::vector<Task> fp{{0, p->T - 1, p->sched.mids[0]}};
+        add_pass(p, all, fp, VEC_FULL_RANGE | VEC_FIRST_PASS);
+    }
+    for (const auto &lvl : p->sched.levels) {
+        const bool root = !first && li == 0;
+        p->lvl_off.push_back((int)mids.size()), p->lvl_cnt.push_back((int)lvl.size());
+        for (const Task &t : lvl) mids.push_back(t.mid);
+        std::vector<Task> mine;
+        if (root) mine = lvl;  // pass 0 of a plan without an N-way pass: the state-sharded one, run by every rank
+        else
+            for (size_t t = 0; t < lvl.size(); ++t)
+                if ((int)(t % (size_t)p->shard_world) == p->shard_rank) mine.push_back(lvl[t]);
+        add_pass(p, all, mine, root ? VEC_FULL_RANGE : 0);  // possibly empty: the rank still takes part in the exchange
+        ++li;
+    }
+    (void)old;
+    FV_CUDA(cudaMemcpyAsync(p->d_vecs, all.data(), all.size() * sizeof(VecDesc), cudaMemcpyHostToDevice, p->model->ctx->stream));
+    FV_CUDA(cudaMalloc(&p->d_lvl_mid, (mids.size() + 1) * sizeof(int32_t)));
+    FV_CUDA(cudaMemcpyAsync(p->d_lvl_mid, mids.data(), mids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, p->model->ctx->stream));
+    FV_CUDA(cudaStreamSynchronize(p->model->ctx->stream));
+    return FLASHV_OK;
+}
+
 extern "C" int flashv_plan_shard_init(flashv_plan *p, int rank, int world)
 {
     if (!p || world < 1 || world > 8 || rank < 0 || rank >= world) {
@@ -293,7 +464,7 @@ extern "C" int flashv_plan_shard_init(flashv_plan *p, int rank, int world)
         set_error("flashv_plan_shard_init: only single-sequence FLASH plans on the persistent engine shard their states");
         return FLASHV_ERR_ARG;
     }
-    if (p->hiC_shard) {
+    if (p->hiC_shard || p->shard_region) {
         set_error("flashv_plan_shard_init: plan is already sharded");
         return FLASHV_ERR_STATE;
     }
@@ -302,32 +473,47 @@ extern "C" int flashv_plan_shard_init(flashv_plan *p, int rank, int world)
     if (world == 1) return FLASHV_OK;
     int rc = shard_build_table(p);
     if (rc != FLASHV_OK) return rc;
-    p->peer_delta[rank] = p->d_delta, p->peer_psi[rank] = p->d_psi;
+    // the region peers store into: exchange words, Ans exchange words, backpointer rows of pass 0
+    const int K = p->model->K, Kp = p->model->Kp;
+    const size_t xch_bytes = (size_t)2 * Kp * 8;
+    const size_t ans_bytes = ((size_t)p->T * 8 + 255) & ~(size_t)255;
+    const size_t psi_bytes = (size_t)p->passes[0].psi_rows * K * (p->psi16 ? 2 : 4) + 64;
+    p->shard_ans_off = xch_bytes, p->shard_psi_off = xch_bytes + ans_bytes;
+    p->shard_region_bytes = xch_bytes + ans_bytes + psi_bytes;
+    FV_CUDA(cudaMalloc(&p->shard_region, p->shard_region_bytes));
+    FV_CUDA(cudaMemsetAsync(p->shard_region, 0, xch_bytes + ans_bytes, p->model->ctx->stream));
+    p->bytes += p->shard_region_bytes;
+    p->peer_region[rank] = p->shard_region;
+    return shard_spread_levels(p);
+}
+
+extern "C" int flashv_plan_shard_buffers(flashv_plan *p, void **region_base, size_t *region_bytes)
+{
+    if (!p || !region_base || !p->shard_region) {
+        set_error("flashv_plan_shard_buffers: plan is not sharded");
+        return FLASHV_ERR_ARG;
+    }
+    *region_base = p->shard_region;
+    if (region_bytes) *region_bytes = p->shard_region_bytes;
     return FLASHV_OK;
 }
 
-extern "C" int flashv_plan_shard_buffers(flashv_plan *p, void **delta_base, void **psi_base)
+extern "C" int flashv_plan_shard_ipc_handle(flashv_plan *p, void *out64)
 {
-    if (!p || !delta_base || !psi_base) return FLASHV_ERR_ARG;
-    *delta_base = p->d_delta, *psi_base = p->d_psi;
-    return FLASHV_OK;
-}
-
-extern "C" int flashv_plan_shard_ipc_handles(flashv_plan *p, void *out128)
-{
-    if (!p || !out128) return FLASHV_ERR_ARG;
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "two handles fill 128 bytes");
+    if (!p || !out64 || !p->shard_region) {
+        set_error("flashv_plan_shard_ipc_handle: plan is not sharded");
+        return FLASHV_ERR_ARG;
+    }
     FV_CUDA(cudaSetDevice(p->model->ctx->device));
-    cudaIpcMemHandle_t h[2];
-    FV_CUDA(cudaIpcGetMemHandle(&h[0], p->d_delta));
-    FV_CUDA(cudaIpcGetMemHandle(&h[1], p->d_psi));
-    memcpy(out128, h, sizeof(h));
+    cudaIpcMemHandle_t h;
+    FV_CUDA(cudaIpcGetMemHandle(&h, p->shard_region));
+    memcpy(out64, &h, sizeof(h));
     return FLASHV_OK;
 }
 
-extern "C" int flashv_plan_shard_set_peer(flashv_plan *p, int peer_rank, int peer_device, void *delta_base, void *psi_base)
+extern "C" int flashv_plan_shard_set_peer(flashv_plan *p, int peer_rank, int peer_device, void *region_base)
 {
-    if (!p || peer_rank < 0 || peer_rank >= p->shard_world || !delta_base || !psi_base) {
+    if (!p || !p->shard_region || peer_rank < 0 || peer_rank >= p->shard_world || !region_base) {
         set_error("flashv_plan_shard_set_peer: bad argument");
         return FLASHV_ERR_ARG;
     }
@@ -338,23 +524,22 @@ extern "C" int flashv_plan_shard_set_peer(flashv_plan *p, int peer_rank, int pee
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
         cudaGetLastError();
     }
-    p->peer_delta[peer_rank] = (float *)delta_base, p->peer_psi[peer_rank] = psi_base;
+    p->peer_region[peer_rank] = (unsigned char *)region_base;
     return FLASHV_OK;
 }
 
-extern "C" int flashv_plan_shard_open_peer(flashv_plan *p, int peer_rank, const void *handles128)
+extern "C" int flashv_plan_shard_open_peer(flashv_plan *p, int peer_rank, const void *handle64)
 {
-    if (!p || peer_rank < 0 || peer_rank >= p->shard_world || !handles128 || peer_rank == p->shard_rank) {
+    if (!p || !p->shard_region || peer_rank < 0 || peer_rank >= p->shard_world || !handle64 || peer_rank == p->shard_rank) {
         set_error("flashv_plan_shard_open_peer: bad argument");
         return FLASHV_ERR_ARG;
     }
     FV_CUDA(cudaSetDevice(p->model->ctx->device));
-    cudaIpcMemHandle_t h[2];
-    memcpy(h, handles128, sizeof(h));
-    void *d = nullptr, *s = nullptr;
-    FV_CUDA(cudaIpcOpenMemHandle(&d, h[0], cudaIpcMemLazyEnablePeerAccess));
-    FV_CUDA(cudaIpcOpenMemHandle(&s, h[1], cudaIpcMemLazyEnablePeerAccess));
-    p->peer_delta[peer_rank] = (float *)d, p->peer_psi[peer_rank] = s, p->peer_ipc[peer_rank] = true;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void *d = nullptr;
+    FV_CUDA(cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess));
+    p->peer_region[peer_rank] = (unsigned char *)d, p->peer_ipc[peer_rank] = true;
     return FLASHV_OK;
 }
 
@@ -388,12 +573,36 @@ extern "C" int flashv_plan_run(flashv_plan *p)
     flashv_ctx *ctx = p->model->ctx;
     FV_CUDA(cudaSetDevice(ctx->device));
     p->launches = 0;
+    const bool sharded = p->shard_world > 1;
+    if (sharded) {
+        // Peers store into this plan's region during a run, and the tags that make those stores
+        // self-validating count runs: every rank must have finished run n before any starts run n+1
+        // (include/flashv.h).  What can be checked locally is that this rank's previous work is done.
+        if (cudaStreamQuery(ctx->stream) == cudaErrorNotReady) {
+            set_error("flashv_plan_run: a state-sharded plan needs an idle stream (sync, then barrier across ranks, then run)");
+            return FLASHV_ERR_STATE;
+        }
+        cudaGetLastError();
+        for (int r = 0; r < p->shard_world; ++r)
+            if (!p->peer_region[r]) {
+                set_error("flashv_plan_run: peer %d of the sharded plan has not been connected", r);
+                return FLASHV_ERR_STATE;
+            }
+        ++p->shard_run;
+    }
     FV_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     bool first = true;
-    for (const Pass &ps : p->passes) {
-        int rc = p->B > 0 ? bs_run_pass(p, ps) : flash_run_pass(p, ps, first);
+    const int first_level_pass = p->sched.first_pass ? 1 : 0;
+    for (size_t pi = 0; pi < p->passes.size(); ++pi) {
+        const Pass &ps = p->passes[pi];
+        int rc = FLASHV_OK;
+        if (ps.nvec > 0) rc = p->B > 0 ? bs_run_pass(p, ps) : flash_run_pass(p, ps, first);
         if (rc != FLASHV_OK) return rc;
         first = false;
+        if (sharded && pi > 0) {  // pass 0 is the state-sharded one: every rank already holds its results
+            rc = shard_ans_exchange(p, (int)pi - first_level_pass);
+            if (rc != FLASHV_OK) return rc;
+        }
     }
     FV_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     p->ran = true;

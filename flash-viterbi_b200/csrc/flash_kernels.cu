@@ -84,7 +84,7 @@ __device__ __forceinline__ void tile_accumulate(float (&cm)[RI][QB][4], const fl
 
 // ---- engine STEP: one launch per trellis step ------------------------------------------------
 // A block of NWARP warps keeps delta of QB vectors in shared memory and walks over tiles of
-// NWARP*RI destination columns (grid.x workers per vector group, grid.y vector groups).  A warp
+// NWARP*RI destination columns (grid.y workers per vector group, grid.x vector groups).  A warp
 // owns RI columns of the tile: lane l reads hiT[i][4*(l+32u) .. +3] as one 128-bit load per u, so
 // a column streams as contiguous 512-byte requests straight from L2/HBM into registers, and every
 // hi value meets QB delta vectors, every delta value RI columns (an RI x QB register tile of
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
     extern __shared__ float4 sdelta4[];
     constexpr int NT = NWARP * 32;
     const int Kp4 = a.Kp >> 2;
-    const int v0 = blockIdx.y * QB;
+    const int v0 = blockIdx.x * QB;  // vector groups on x (no 65535 cap), column workers on y
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int q = 0; q < QB; ++q) {
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
     }
 
     const int ntiles = (a.K + NWARP * RI - 1) / (NWARP * RI);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
         const int ibase = (tile * NWARP + warp) * RI;
         if (ibase >= a.K) continue;  // warp-uniform; no block-wide barrier below
         int col_i[RI];
@@ -378,7 +378,8 @@ static cudaError_t launch_step(const StepArgs &a, int nact, int sm_count, cudaSt
     int workers = (sm_count * per_sm) / ngroups;  // round down: one extra block would cost a whole second wave
     if (workers > ntiles) workers = ntiles;
     if (workers < 1) workers = 1;
-    dim3 grid(workers, ngroups);
+    if (workers > 65535) workers = 65535;
+    dim3 grid(ngroups, workers);
     k_flash_step<QB, RI, NWARP><<<grid, NWARP * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
@@ -465,10 +466,10 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
     if (pass.nvec == 1 && pass.max_steps >= 16 && win_rows >= 4) {
         const size_t smem = (size_t)win_rows * row_bytes + 32;
         FV_CUDA(cudaFuncSetAttribute(k_flash_backtrack_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        k_flash_backtrack_staged<<<1, 1024, smem, st>>>(vecs, p->d_psi, p->psi16, K, T, p->d_ismid, p->d_endstate, p->d_ans,
+        k_flash_backtrack_staged<<<1, 1024, smem, st>>>(vecs, pass_psi(p, pass), p->psi16, K, T, p->d_ismid, p->d_endstate, p->d_ans,
                                                       win_rows);
     } else {
-        k_flash_backtrack<<<(pass.nvec + 127) / 128, 128, 0, st>>>(vecs, pass.nvec, p->d_psi, p->psi16, K, T, p->d_ismid,
+        k_flash_backtrack<<<(pass.nvec + 127) / 128, 128, 0, st>>>(vecs, pass.nvec, pass_psi(p, pass), p->psi16, K, T, p->d_ismid,
                                                                    p->d_endstate, p->d_ans);
     }
     FV_CUDA(cudaGetLastError());

@@ -77,12 +77,12 @@ __device__ __forceinline__ unsigned long long now_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void watchdog(uint32_t spins, unsigned long long &t0)
+__device__ __forceinline__ void watchdog(uint32_t spins, unsigned long long &t0, unsigned long long limit_ns = WATCHDOG_NS)
 {
     if ((spins & 1023u) == 1023u) {
         const unsigned long long t = now_ns();
         if (t0 == 0) t0 = t;
-        else if (t - t0 > WATCHDOG_NS) __trap();
+        else if (t - t0 > limit_ns) __trap();
     }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
@@ -176,6 +176,7 @@ struct PersistArgs {
     int psi16;
     int nstage;
     int l2_hint;
+    unsigned long long watchdog_ns;  // how long a poll for delta words may last before the kernel traps (longer across GPUs)
     long long *trace;  // optional [TRACE_STEPS][grid][2 warps][TRACE_PTS] clock64 samples (FLASHV_TRACE_FILE), else null
 };
 
@@ -253,7 +254,7 @@ __device__ __forceinline__ void delta_wait_load(const PersistArgs &a, int s, flo
                         if ((unsigned)(w0[e] >> 32) == want && (k + 1 >= a.K || (unsigned)(w1[e] >> 32) == want))
                             pending &= ~(1u << e);
                     }
-                if (pending) watchdog(spins * 64u + 63u, tw);
+                if (pending) watchdog(spins * 64u + 63u, tw, a.watchdog_ns);
             }
 #pragma unroll
             for (int e = 0; e < NB; ++e) {
@@ -638,6 +639,12 @@ static size_t persist_smem(int Kp, int nstage)
     return CTRL_BYTES + (size_t)Kp * 4 + (size_t)nstage * TILE_RW * TILE_CH * 4;
 }
 
+// Largest padded K whose delta vector plus two ring stages fit the shared memory of one CTA.
+bool persistent_engine_fits(const flashv_ctx *ctx, int Kp)
+{
+    return ctx->coop && persist_smem(Kp, 2) <= (size_t)ctx->smem_optin;
+}
+
 static int env_int(const char *name, int dflt)
 {
     const char *e = getenv(name);
@@ -699,6 +706,13 @@ static int launch_persist(flashv_model *m, PersistArgs &a)
     return FLASHV_OK;
 }
 
+static unsigned long long watchdog_limit_ns(bool cross_gpu)
+{
+    // A rank that launches late (first-call module load, a slow host) must not trap its peers.
+    const int ms = env_int("FLASHV_WATCHDOG_MS", cross_gpu ? 30000 : 4000);
+    return (unsigned long long)(ms < 100 ? 100 : ms) * 1000000ull;
+}
+
 int persistent_pass(flashv_plan *p, const Pass &pass)
 {
     flashv_model *m = p->model;
@@ -708,37 +722,88 @@ int persistent_pass(flashv_plan *p, const Pass &pass)
     a.ob = p->d_ob;
     a.L = vd.L, a.nsteps = vd.R - vd.L, a.mid = vd.mid, a.psi_row = vd.psi_row;
     a.d_init = p->d_delta, a.d_final = p->d_delta + (size_t)p->max_vec * m->Kp;
-    a.xch = reinterpret_cast<unsigned long long *>(p->d_delta + (size_t)2 * p->max_vec * m->Kp);
-    a.psi = p->d_psi, a.psi16 = p->psi16;
-    a.epoch = (++p->run_epoch) & 0xffffu;
-    if (a.epoch == 0) a.epoch = (++p->run_epoch) & 0xffffu;  // tag 0 is what a fresh buffer holds
-    // Only the plan's first pass is sharded (the N-way pass, or the root task): it is the one long
-    // single-vector pass, and it is the only time every GPU is known to be in lock-step.  Later
-    // single-vector passes are a step or two long and run locally, so no GPU ever writes into a
-    // peer's backpointer store while that peer may still be walking it.
-    if (p->shard_world > 1 && &pass == &p->passes[0]) {
+    a.psi16 = p->psi16;
+    // Only the plan's pass 0 is sharded (the N-way pass, or the root task): it is the one long
+    // single-vector pass.  It uses the plan's shard region — exchange words and backpointer rows that
+    // no local pass touches — and tags its words with the run count, which is the same on every rank.
+    if (pass_is_sharded(p, pass)) {
         // state-sharded: this GPU owns the columns [shard_c0, shard_c0 + shard_ncol) and publishes
-        // into every GPU's buffers (same offsets in every plan: identical plan parameters)
+        // into every GPU's region (same offsets in every plan: identical plan parameters)
         if (a.nsteps >= 65536) {
             set_error("state-sharded pass: more than 65535 steps");
             return FLASHV_ERR_ARG;
         }
+        a.epoch = p->shard_run % 65535u + 1u;
         a.hiC = p->hiC_shard, a.col_begin = p->shard_c0, a.ncol = p->shard_ncol, a.npeer = p->shard_world;
+        a.xch = reinterpret_cast<unsigned long long *>(p->shard_region);
+        a.psi = p->shard_region + p->shard_psi_off;
         for (int r = 0; r < p->shard_world; ++r) {
-            if (!p->peer_delta[r] || !p->peer_psi[r]) {
-                set_error("state-sharded pass: peer %d has not been connected", r);
-                return FLASHV_ERR_STATE;
-            }
-            a.xch_peer[r] = reinterpret_cast<unsigned long long *>(p->peer_delta[r] + (size_t)2 * p->max_vec * m->Kp);
-            a.psi_peer[r] = p->peer_psi[r];
+            a.xch_peer[r] = reinterpret_cast<unsigned long long *>(p->peer_region[r]);
+            a.psi_peer[r] = p->peer_region[r] + p->shard_psi_off;
         }
+        a.watchdog_ns = watchdog_limit_ns(true);
     } else {
+        a.epoch = (++p->run_epoch) & 0xffffu;
+        if (a.epoch == 0) a.epoch = (++p->run_epoch) & 0xffffu;  // tag 0 is what a fresh buffer holds
+        a.xch = reinterpret_cast<unsigned long long *>(p->d_delta + (size_t)2 * p->max_vec * m->Kp);
+        a.psi = p->d_psi;
         a.hiC = m->hiC, a.col_begin = 0, a.ncol = m->K, a.npeer = 1;
         a.xch_peer[0] = a.xch, a.psi_peer[0] = a.psi;
+        a.watchdog_ns = watchdog_limit_ns(false);
     }
     int rc = launch_persist(m, a);
     if (rc == FLASHV_OK) p->launches += 1;
     return rc;
+}
+
+// ---- task-tree levels of a state-sharded plan: every rank ran its share of the level's tasks; now every
+// rank needs all of the level's Ans entries (the next level restarts from Ans[L-1] and ends in Ans[R],
+// F:220, F:248).  Same idea as the delta exchange: each entry travels as ONE self-validating 64-bit
+// word {Ans value, run|level tag}, stored by its owner into every rank's region and polled locally.
+struct AnsXchArgs {
+    const int32_t *mids;  // midpoints of the level's tasks, all ranks', in level order; task t belongs to rank t % world
+    int cnt, rank, world;
+    int32_t *ans;
+    unsigned tag;
+    unsigned long long *xch_peer[8];  // every rank's Ans exchange words [T] (entry `rank` is the local one)
+    unsigned long long watchdog_ns;
+};
+
+__global__ void __launch_bounds__(256) k_ans_exchange(const AnsXchArgs a)
+{
+    for (int t = threadIdx.x; t < a.cnt; t += blockDim.x)
+        if (t % a.world == a.rank) {
+            const int mid = a.mids[t];
+            const unsigned long long w = ((unsigned long long)a.tag << 32) | (unsigned long long)(unsigned)a.ans[mid];
+            for (int r = 0; r < a.world; ++r) asm volatile("st.global.u64 [%0], %1;" ::"l"(a.xch_peer[r] + mid), "l"(w) : "memory");
+        }
+    const unsigned long long *mine = a.xch_peer[a.rank];
+    for (int t = threadIdx.x; t < a.cnt; t += blockDim.x) {
+        const int mid = a.mids[t];
+        unsigned long long w, t0 = 0;
+        for (uint32_t spins = 0;; ++spins) {
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(mine + mid) : "memory");
+            if ((unsigned)(w >> 32) == a.tag) break;
+            watchdog(spins * 16u + 15u, t0, a.watchdog_ns);
+        }
+        a.ans[mid] = (int32_t)(unsigned)w;
+    }
+}
+
+int shard_ans_exchange(flashv_plan *p, int level)
+{
+    if (level < 0 || level >= (int)p->lvl_cnt.size()) return FLASHV_OK;
+    AnsXchArgs a;
+    a.mids = p->d_lvl_mid + p->lvl_off[level], a.cnt = p->lvl_cnt[level];
+    a.rank = p->shard_rank, a.world = p->shard_world, a.ans = p->d_ans;
+    a.tag = ((p->shard_run & 0x3ffffffu) << 6) | (unsigned)(level + 1);
+    for (int r = 0; r < p->shard_world; ++r)
+        a.xch_peer[r] = reinterpret_cast<unsigned long long *>(p->peer_region[r] + p->shard_ans_off);
+    a.watchdog_ns = watchdog_limit_ns(true);
+    k_ans_exchange<<<1, 256, 0, p->model->ctx->stream>>>(a);
+    FV_CUDA(cudaGetLastError());
+    ++p->launches;
+    return FLASHV_OK;
 }
 
 // ---- state sharding: this GPU's column slice of the tiled table ------------------------
@@ -779,6 +844,7 @@ int persistent_single_step(flashv_model *m, const float *d_in_dev, int o, float 
     a.xch = reinterpret_cast<unsigned long long *>(m->scratch_x);
     a.psi = psi_dev, a.psi16 = 0;
     a.xch_peer[0] = a.xch, a.psi_peer[0] = a.psi;
+    a.watchdog_ns = watchdog_limit_ns(false);
     return launch_persist(m, a);
 }
 

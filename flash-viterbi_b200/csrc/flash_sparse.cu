@@ -23,6 +23,11 @@
 //   F: = /root/reference/src/FLASH_Viterbi_multithread.c   D: = generate_data/data_script.py
 #include <stdlib.h>
 
+#include <algorithm>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
 #include "flashv_internal.h"
 #include "trellis_common.cuh"
 
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_flash_sparse_pass(const Spars
 }
 
 // ---- one step of a level of the task tree (many vectors) over the same edge lists -----------------
-// grid (column workers, vector groups): a CTA stages delta of SQ vectors in shared memory and its
+// grid (vector groups, column workers): a CTA stages delta of SQ vectors in shared memory and its
 // warps walk destination columns; a column's edge list is read once (coalesced) and applied to all
 // SQ vectors with the exact chain, first maximum kept lane-locally in ascending k.
 constexpr int SQ = 8;  // vectors per group
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(512) k_flash_sparse_step(const SparseStepArgs 
     extern __shared__ float4 sp_sdelta4[];
     float *sdelta = reinterpret_cast<float *>(sp_sdelta4);  // [SQ][Kp]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    const int v0 = blockIdx.y * SQ;
+    const int v0 = blockIdx.x * SQ;  // vector groups on x (no 65535 cap), column workers on y
     const int Kp4 = a.Kp >> 2;
 #pragma unroll
     for (int q = 0; q < SQ; ++q) {
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(512) k_flash_sparse_step(const SparseStepArgs 
         }
     }
     __syncthreads();
-    for (int i = blockIdx.x * nwarp + warp; i < a.K; i += gridDim.x * nwarp) {
+    for (int i = blockIdx.y * nwarp + warp; i < a.K; i += gridDim.y * nwarp) {
         float tmp[SQ];
         Best b[SQ];
 #pragma unroll
@@ -249,49 +254,144 @@ int sparse_level_step(flashv_plan *p, const Pass &pass, int s, int nact, const f
     int workers = (ctx->sm_count * per_sm) / ngroups;
     const int max_workers = (m->K + 15) / 16;  // 16 warps per CTA, at least one column each
     workers = workers < 1 ? 1 : (workers > max_workers ? max_workers : workers);
-    k_flash_sparse_step<<<dim3(workers, ngroups), 512, smem, ctx->stream>>>(a);
+    k_flash_sparse_step<<<dim3(ngroups, workers), 512, smem, ctx->stream>>>(a);
     FV_CUDA(cudaGetLastError());
     ++p->launches;
     return FLASHV_OK;
 }
 
-// ---- host side: the in-edge lists, built once per model from the host log table -------------------
-int sparse_build(flashv_model *m, const double *hLA)
+// ---- the edge lists, built once per model ON THE DEVICE from the double log table ---------------------
+// (the host only computes logarithms; everything that is a re-arrangement of them runs here, so a
+// model whose rows were computed by several ranks and assembled over NVLink gets the same lists)
+//
+// In-edge lists (by destination i, ascending source k): the source axis is cut into CS slices; thread
+// (i, slice) counts, an exclusive scan over the (i-major, slice-minor) counts gives every thread its
+// first entry — which is already the list order — and a second walk fills.
+constexpr int CS = 32;
+
+__global__ void k_csc_count(const double *__restrict__ LAd, int K, int kslice, int *__restrict__ cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, sl = blockIdx.y;
+    if (i >= K) return;
+    const int k1 = min(K, (sl + 1) * kslice);
+    int c = 0;
+    for (int k = sl * kslice; k < k1; ++k) c += LAd[(size_t)k * K + i] > -INFINITY;
+    cnt[(size_t)i * CS + sl] = c;
+}
+
+__global__ void k_csc_fill(const double *__restrict__ LAd, int K, int kslice, const int *__restrict__ off,
+                           uint16_t *__restrict__ ck, double *__restrict__ cla, int *__restrict__ ptr, int nnz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, sl = blockIdx.y;
+    if (i >= K) return;
+    int e = off[(size_t)i * CS + sl];
+    if (sl == 0) ptr[i] = e;
+    if (sl == 0 && i == K - 1) ptr[K] = nnz;
+    const int k1 = min(K, (sl + 1) * kslice);
+    for (int k = sl * kslice; k < k1; ++k) {
+        const double v = LAd[(size_t)k * K + i];
+        if (v > -INFINITY) ck[e] = (uint16_t)k, cla[e] = v, ++e;
+    }
+}
+
+// Out-edge lists (by source k, ascending destination i), one warp per row.
+__global__ void k_csr_count(const double *__restrict__ LAd, int K, int *__restrict__ cnt)
+{
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= K) return;
+    int c = 0;
+    for (int i = lane; i < K; i += 32) c += LAd[(size_t)k * K + i] > -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+    if (lane == 0) cnt[k] = c;
+}
+
+__global__ void k_csr_fill(const double *__restrict__ LAd, int K, const int *__restrict__ rowstart,
+                           uint16_t *__restrict__ ri, double *__restrict__ rla)
+{
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= K) return;
+    int e = rowstart[k];
+    for (int i0 = 0; i0 < K; i0 += 32) {
+        const int i = i0 + lane;
+        const double v = i < K ? LAd[(size_t)k * K + i] : -INFINITY;
+        const unsigned m = __ballot_sync(FULL_MASK, v > -INFINITY);
+        if (v > -INFINITY) {
+            const int at = e + __popc(m & ((1u << lane) - 1u));
+            ri[at] = (uint16_t)i, rla[at] = v;
+        }
+        e += __popc(m);
+    }
+}
+
+// cut[k][q] = first entry of row k whose destination is >= q*per8 (q = 0..8): the ranges a cluster's CTAs own
+__global__ void k_csr_cuts(const uint16_t *__restrict__ ri, const int *__restrict__ rowstart, int K, int nnz, int per8,
+                           int *__restrict__ cut)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= K * 9) return;
+    const int k = t / 9, q = t - 9 * k;
+    int lo = rowstart[k], hi = k + 1 < K ? rowstart[k + 1] : nnz;
+    const int want = q * per8;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)ri[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    cut[t] = lo;
+}
+
+static int exclusive_scan(int *d_in, int *d_out, int n, cudaStream_t st)
+{
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    FV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_in, d_out, n, st));
+    FV_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_in, d_out, n, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    FV_CUDA(e);
+    return FLASHV_OK;
+}
+
+int sparse_build(flashv_model *m)
 {
     const int K = m->K;
     if (K >= 65536) return FLASHV_OK;  // 16-bit source indices: larger models keep the dense engines only
     if (const char *e = getenv("FLASHV_NO_SPARSE"))
         if (atoi(e) != 0) return FLASHV_OK;  // skip the edge lists (saves their build time and memory on very large models)
-    std::vector<int> ptr((size_t)K + 1, 0);
-    for (int k = 0; k < K; ++k) {
-        const double *row = hLA + (size_t)k * K;
-        for (int i = 0; i < K; ++i)
-            if (row[i] > -INFINITY) ++ptr[i + 1];
-    }
-    for (int i = 0; i < K; ++i) ptr[i + 1] += ptr[i];
-    const size_t nnz = (size_t)ptr[K];
-    if (nnz == 0 || nnz > (size_t)K * K / 2) return FLASHV_OK;  // dense enough that the dense engines are the better fit
-    std::vector<uint16_t> ck(nnz);
-    std::vector<double> cla(nnz);
-    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
-    for (int k = 0; k < K; ++k) {  // ascending k per column by construction
-        const double *row = hLA + (size_t)k * K;
-        for (int i = 0; i < K; ++i)
-            if (row[i] > -INFINITY) {
-                const int e = fill[i]++;
-                ck[e] = (uint16_t)k, cla[e] = row[i];
-            }
-    }
     flashv_ctx *ctx = m->ctx;
-    FV_CUDA(cudaMalloc(&m->csc_ptr, ((size_t)K + 1) * sizeof(int)));
-    FV_CUDA(cudaMalloc(&m->csc_k, nnz * sizeof(uint16_t)));
-    FV_CUDA(cudaMalloc(&m->csc_la, nnz * sizeof(double)));
-    FV_CUDA(cudaMemcpyAsync(m->csc_ptr, ptr.data(), ((size_t)K + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    FV_CUDA(cudaMemcpyAsync(m->csc_k, ck.data(), nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-    FV_CUDA(cudaMemcpyAsync(m->csc_la, cla.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    FV_CUDA(cudaStreamSynchronize(ctx->stream));  // the vectors are on this frame
+    cudaStream_t st = ctx->stream;
+    const int kslice = (K + CS - 1) / CS;
+    const size_t ncnt = (size_t)K * CS;
+    int *d_cnt = nullptr, *d_off = nullptr;
+    FV_CUDA(cudaMalloc(&d_cnt, (ncnt + K) * sizeof(int)));
+    FV_CUDA(cudaMalloc(&d_off, (ncnt + K) * sizeof(int)));
+    int rc = FLASHV_OK;
+    auto done = [&](int code) {
+        cudaFree(d_cnt), cudaFree(d_off);
+        return code;
+    };
+    k_csc_count<<<dim3((K + 127) / 128, CS), 128, 0, st>>>(m->LAd, K, kslice, d_cnt);
+    if ((rc = exclusive_scan(d_cnt, d_off, (int)ncnt, st)) != FLASHV_OK) return done(rc);
+    int last[2];
+    cudaError_t e = cudaMemcpy(&last[0], d_off + ncnt - 1, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&last[1], d_cnt + ncnt - 1, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return done(cuda_fail(e, "edge count", __FILE__, __LINE__));
+    const size_t nnz = (size_t)last[0] + (size_t)last[1];
+    if (nnz == 0 || nnz > (size_t)K * K / 2) return done(FLASHV_OK);  // dense enough that the dense engines are the better fit
+
+#define SB_CUDA(call)                                                                  \
+    if ((e = (call)) != cudaSuccess) return done(cuda_fail(e, #call, __FILE__, __LINE__));
+    SB_CUDA(cudaMalloc(&m->csc_ptr, ((size_t)K + 1) * sizeof(int)));
+    SB_CUDA(cudaMalloc(&m->csc_k, nnz * sizeof(uint16_t)));
+    SB_CUDA(cudaMalloc(&m->csc_la, nnz * sizeof(double)));
+    k_csc_fill<<<dim3((K + 127) / 128, CS), 128, 0, st>>>(m->LAd, K, kslice, d_off, m->csc_k, m->csc_la, m->csc_ptr, (int)nnz);
+    SB_CUDA(cudaGetLastError());
     m->csc_nnz = (long long)nnz;
     // the largest per-CTA edge count for the grid the pass kernel uses
+    std::vector<int> ptr((size_t)K + 1);
+    SB_CUDA(cudaMemcpyAsync(ptr.data(), m->csc_ptr, ptr.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
     const int G = ctx->sm_count < K ? ctx->sm_count : K;
     int worst = 0;
     for (int b = 0; b < G; ++b) {
@@ -303,31 +403,21 @@ int sparse_build(flashv_model *m, const double *hLA)
 
     // The same edges by SOURCE for FLASH-BS (a step only looks at the out-edges of the B beam states),
     // with every row cut at the 8 destination-range boundaries q*ceil(K/8) a cluster's CTAs own.
-    {
-        const int per8 = (K + 7) / 8;
-        std::vector<int> cut((size_t)K * 9);
-        std::vector<uint16_t> ri(nnz);
-        std::vector<double> rla(nnz);
-        size_t e = 0;
-        for (int k = 0; k < K; ++k) {
-            const double *row = hLA + (size_t)k * K;
-            int q = 0;
-            for (int i = 0; i < K; ++i) {
-                while (q < 9 && i >= q * per8) cut[(size_t)k * 9 + q++] = (int)e;
-                if (row[i] > -INFINITY) ri[e] = (uint16_t)i, rla[e] = row[i], ++e;
-            }
-            while (q < 9) cut[(size_t)k * 9 + q++] = (int)e;
-        }
-        FV_CUDA(cudaMalloc(&m->csr_cut, cut.size() * sizeof(int)));
-        FV_CUDA(cudaMalloc(&m->csr_i, nnz * sizeof(uint16_t)));
-        FV_CUDA(cudaMalloc(&m->csr_la, nnz * sizeof(double)));
-        FV_CUDA(cudaMemcpyAsync(m->csr_cut, cut.data(), cut.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        FV_CUDA(cudaMemcpyAsync(m->csr_i, ri.data(), nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-        FV_CUDA(cudaMemcpyAsync(m->csr_la, rla.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        FV_CUDA(cudaStreamSynchronize(ctx->stream));
-        m->bytes += cut.size() * sizeof(int) + nnz * (sizeof(uint16_t) + sizeof(double));
-    }
-    return FLASHV_OK;
+    int *d_rowcnt = d_cnt + ncnt, *d_rowstart = d_off + ncnt;
+    k_csr_count<<<(K + 7) / 8, 256, 0, st>>>(m->LAd, K, d_rowcnt);
+    SB_CUDA(cudaGetLastError());
+    if ((rc = exclusive_scan(d_rowcnt, d_rowstart, K, st)) != FLASHV_OK) return done(rc);
+    SB_CUDA(cudaMalloc(&m->csr_cut, (size_t)K * 9 * sizeof(int)));
+    SB_CUDA(cudaMalloc(&m->csr_i, nnz * sizeof(uint16_t)));
+    SB_CUDA(cudaMalloc(&m->csr_la, nnz * sizeof(double)));
+    k_csr_fill<<<(K + 7) / 8, 256, 0, st>>>(m->LAd, K, d_rowstart, m->csr_i, m->csr_la);
+    SB_CUDA(cudaGetLastError());
+    k_csr_cuts<<<(K * 9 + 255) / 256, 256, 0, st>>>(m->csr_i, d_rowstart, K, (int)nnz, (K + 7) / 8, m->csr_cut);
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(st));
+#undef SB_CUDA
+    m->bytes += (size_t)K * 9 * sizeof(int) + nnz * (sizeof(uint16_t) + sizeof(double));
+    return done(FLASHV_OK);
 }
 
 bool sparse_engine_available(const flashv_model *m) { return m->csc_ptr != nullptr; }

@@ -79,6 +79,10 @@ struct flashv_ctx {
     // pinned staging for the one-call API
     int32_t *h_stage = nullptr;
     size_t h_stage_bytes = 0;
+    // pinned double buffer + its events for the chunked log-table upload of flashv_model_create (tables.cu)
+    void *h_prep[2] = {nullptr, nullptr};
+    size_t h_prep_bytes = 0;
+    cudaEvent_t ev_prep[2] = {nullptr, nullptr};
 };
 
 struct flashv_model {
@@ -106,6 +110,9 @@ struct flashv_model {
     void *scratch_x = nullptr;    // test hooks: exchange buffers [2][Kp] x 8 B
     size_t bytes = 0;
     double prep_ms = 0;
+    int row_lo = 0, row_hi = 0;   // rows of LAd whose logarithms this process computed (all of them unless the model was created in parts)
+    bool ready = false;           // layouts built: the model can decode
+    int part_rank = 0, part_world = 1;  // flashv_model_create_rows: which rows are local
     std::vector<flashv_plan *> plan_cache;  // owned; used by the one-call decodes
 };
 
@@ -130,10 +137,16 @@ struct flashv_plan {
     int shard_rank = 0, shard_world = 1;
     int shard_c0 = 0, shard_ncol = 0;   // destination columns this GPU owns
     float *hiC_shard = nullptr;         // their slice of the tiled table
-    float *peer_delta[8] = {};          // every GPU's d_delta block (own entry included)
-    void *peer_psi[8] = {};             // every GPU's backpointer store
+    // One device region per sharded plan holds everything peers store into, and nothing the local
+    // passes reuse: [exchange words 2 x Kp x 8 B][Ans exchange words T x 8 B][backpointer rows of pass 0]
+    unsigned char *shard_region = nullptr;
+    size_t shard_region_bytes = 0, shard_ans_off = 0, shard_psi_off = 0;
+    unsigned char *peer_region[8] = {};  // every GPU's region (own entry included)
     bool peer_ipc[8] = {};              // opened with cudaIpcOpenMemHandle (to be closed)
-    unsigned run_epoch = 0;             // tags the exchange words of one run
+    unsigned shard_run = 0;             // counts the runs of a sharded plan: the same on every rank, tags all cross-GPU words
+    int32_t *d_lvl_mid = nullptr;       // midpoints of every task, level after level (all ranks' tasks): the Ans entries a level produces
+    std::vector<int> lvl_off, lvl_cnt;  // per tree level: offset into d_lvl_mid, task count
+    unsigned run_epoch = 0;             // tags the exchange words of the local (unsharded) persistent passes
     // FLASH-BS
     float *d_bs_score = nullptr;  // [max_vec][Kp]
     size_t bytes = 0;
@@ -146,12 +159,14 @@ struct flashv_plan {
 // ---- kernels / stages (defined in the .cu files) -------------------------------------------
 namespace flashv {
 
-int tables_build(flashv_model *m, const float *A, const float *B, const float *Pi);
+int tables_alloc(flashv_model *m);
+int tables_logs(flashv_model *m, const float *A, const float *B, const float *Pi, int row_lo, int row_hi, int share);
+int tables_layouts(flashv_model *m);
 void build_tiled_slice(const double *LAd, float *hiC, int K, int Kp, int col_begin, int ncol, int G, cudaStream_t st);
 int shard_build_table(flashv_plan *p);
 
 int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it);
-int sparse_build(flashv_model *m, const double *hLA);               // flash_sparse.cu
+int sparse_build(flashv_model *m);                                  // flash_sparse.cu: edge lists from the device table
 bool sparse_engine_available(const flashv_model *m);
 int sparse_pass(flashv_plan *p, const Pass &pass);
 int sparse_level_step(flashv_plan *p, const Pass &pass, int s, int nact, const float *din, float *dout);
@@ -159,6 +174,14 @@ bool group_engine_fits(const flashv_model *m);                       // flash_gr
 int group_run_pass(flashv_plan *p, const Pass &pass, float *dfinal);  // flash_group.cu
 constexpr int GROUP_MAX_KP = 1536;  // largest padded K the group engine's shared-memory buffers hold
 int bs_run_pass(flashv_plan *p, const Pass &pass);
+bool persistent_engine_fits(const flashv_ctx *ctx, int Kp);           // flash_persistent.cu
+constexpr int STEP_MAX_KP = 220 * 1024 / 4;  // the per-step kernels keep one delta vector (Kp floats) in shared memory
+int shard_ans_exchange(flashv_plan *p, int level);                    // flash_persistent.cu: Ans entries of a level to every rank
+inline bool pass_is_sharded(const flashv_plan *p, const Pass &pass) { return p->shard_world > 1 && &pass == &p->passes[0]; }
+inline void *pass_psi(const flashv_plan *p, const Pass &pass)
+{
+    return pass_is_sharded(p, pass) ? (void *)(p->shard_region + p->shard_psi_off) : p->d_psi;
+}
 
 int flash_single_step(flashv_model *m, const float *d_in_dev, int o, float *d_out_dev, int32_t *psi_dev, int engine);
 int flash_single_init(flashv_model *m, int prev_state, int o, float *d_out_dev);

@@ -21,6 +21,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <thread>
 #include <vector>
@@ -76,14 +77,42 @@ void build_tiled_slice(const double *LAd, float *hiC, int K, int Kp, int col_beg
     k_build_tiled<<<dim3((ncol + 255) / 256, Kp), 256, 0, st>>>(LAd, hiC, K, Kp, col_begin, ncol, G);
 }
 
-static bool in_unit(const float *p, size_t n)
+static int host_threads(int share)
 {
-    for (size_t i = 0; i < n; ++i)
-        if (!(p[i] >= 0.0f && p[i] <= 1.0f)) return false;
-    return true;
+    int nthr = 0;
+    if (const char *e = getenv("FLASHV_HOST_THREADS")) nthr = atoi(e);
+    if (nthr < 1) {
+        unsigned hw = std::thread::hardware_concurrency();
+        nthr = (int)(hw ? hw : 8) / (share > 1 ? share : 1);  // ranks of one box share its cores
+    }
+    return nthr < 1 ? 1 : (nthr > 64 ? 64 : nthr);
 }
 
-int tables_build(flashv_model *m, const float *A, const float *B, const float *Pi)
+// Device allocations of the tables that exist for every model (the layouts derived from LAd are
+// allocated by tables_layouts()).
+int tables_alloc(flashv_model *m)
+{
+    const int K = m->K, M = m->M, Kp = m->Kp;
+    const size_t nA = (size_t)K * K;
+    FV_CUDA(cudaMalloc(&m->LAd, nA * sizeof(double)));
+    FV_CUDA(cudaMalloc(&m->LBf, (size_t)M * Kp * sizeof(float)));
+    FV_CUDA(cudaMalloc(&m->LBd, (size_t)M * K * sizeof(double)));
+    FV_CUDA(cudaMalloc(&m->LPi, (size_t)K * sizeof(double)));
+    FV_CUDA(cudaMalloc(&m->scratch_f, (size_t)4 * Kp * sizeof(float)));
+    FV_CUDA(cudaMalloc(&m->scratch_i, (size_t)2 * Kp * sizeof(int32_t)));
+    FV_CUDA(cudaMalloc(&m->scratch_x, (size_t)2 * Kp * 8));
+    FV_CUDA(cudaMemsetAsync(m->scratch_f, 0, (size_t)4 * Kp * sizeof(float), m->ctx->stream));
+    m->bytes += nA * sizeof(double) + (size_t)M * Kp * 4 + (size_t)M * K * 8 + (size_t)K * 8 + (size_t)6 * Kp * 4 +
+               (size_t)2 * Kp * 8;
+    return FLASHV_OK;
+}
+
+// Host libm logarithms of the rows [row_lo, row_hi) of A (F:170) and of B and Pi (F:142, F:167),
+// uploaded as they are produced: the host threads fill one pinned staging buffer while the copy
+// engine drains the other, so neither the whole double table (8.6 GB at K=32768) nor a pinned
+// allocation of that size ever exists on the host.  Validation (every entry a probability) rides
+// along in the same pass over A.
+int tables_logs(flashv_model *m, const float *A, const float *B, const float *Pi, int row_lo, int row_hi, int share)
 {
     const int K = m->K, M = m->M, Kp = m->Kp;
     flashv_ctx *ctx = m->ctx;
@@ -91,34 +120,72 @@ int tables_build(flashv_model *m, const float *A, const float *B, const float *P
 
     // The window filter of the trellis kernels relies on every log being <= 0;
     // anything else is not a probability table.  The reference would decode garbage or NaN.
-    if (!in_unit(A, (size_t)K * K) || !in_unit(B, (size_t)K * M) || !in_unit(Pi, (size_t)K)) {
+    auto unit = [](float v) { return v >= 0.0f && v <= 1.0f; };
+    bool ok = true;
+    for (size_t t = 0; t < (size_t)K * M && ok; ++t) ok = unit(B[t]);
+    for (int t = 0; t < K && ok; ++t) ok = unit(Pi[t]);
+    if (!ok) {
         set_error("flashv_model_create: A/B/Pi entries must be finite and inside [0,1]");
         return FLASHV_ERR_DOMAIN;
     }
 
-    const size_t nA = (size_t)K * K;
-    double *hLA = nullptr;
-    if (cudaMallocHost(&hLA, nA * sizeof(double)) != cudaSuccess) {
-        cudaGetLastError();
-        set_error("flashv_model_create: pinned allocation of %zu bytes failed", nA * sizeof(double));
-        return FLASHV_ERR_NOMEM;
+    const size_t row_bytes = (size_t)K * sizeof(double);
+    constexpr size_t STAGE_BYTES = (size_t)16 << 20;
+    int chunk_rows = (int)(STAGE_BYTES / row_bytes);
+    if (chunk_rows < 1) chunk_rows = 1;
+    const size_t stage_bytes = (size_t)chunk_rows * row_bytes;
+    if (ctx->h_prep_bytes < stage_bytes) {
+        for (auto &b : ctx->h_prep)
+            if (b) cudaFreeHost(b), b = nullptr;
+        ctx->h_prep_bytes = 0;
+        for (auto &b : ctx->h_prep)
+            if (cudaMallocHost(&b, stage_bytes) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("flashv_model_create: pinned staging allocation of %zu bytes failed", stage_bytes);
+                return FLASHV_ERR_NOMEM;
+            }
+        ctx->h_prep_bytes = stage_bytes;
     }
-    unsigned hw = std::thread::hardware_concurrency();
-    int nthr = (int)(hw ? hw : 8);
-    if (nthr > 64) nthr = 64;
-    if ((size_t)nthr > (size_t)K) nthr = K;
-    {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < nthr; ++t)
-            pool.emplace_back([=]() {
-                for (int k = t; k < K; k += nthr) {
-                    const float *src = A + (size_t)k * K;
-                    double *dst = hLA + (size_t)k * K;
-                    for (int i = 0; i < K; ++i) dst[i] = log((double)src[i]);  // F:170
-                }
-            });
-        for (auto &th : pool) th.join();
+    const int nthr = host_threads(share);
+    std::atomic<int> bad{0};
+    cudaEvent_t drained[2] = {ctx->ev_prep[0], ctx->ev_prep[1]};
+    int nchunk = 0;
+    for (int r0 = row_lo; r0 < row_hi; r0 += chunk_rows, ++nchunk) {
+        const int r1 = r0 + chunk_rows < row_hi ? r0 + chunk_rows : row_hi;
+        double *stage = reinterpret_cast<double *>(ctx->h_prep[nchunk & 1]);
+        if (nchunk >= 2) FV_CUDA(cudaEventSynchronize(drained[nchunk & 1]));  // the copy that last read this buffer
+        const long long cells = (long long)(r1 - r0) * K;
+        int use = nthr;
+        if ((long long)use * 4096 > cells) use = (int)(cells / 4096) + 1;  // tiny models: not worth the threads
+        auto work = [&](int t) {
+            const long long c0 = cells * t / use, c1 = cells * (t + 1) / use;
+            const float *src = A + (size_t)r0 * K;
+            bool good = true;
+            for (long long c = c0; c < c1; ++c) {
+                const float v = src[c];
+                good &= (v >= 0.0f && v <= 1.0f);
+                stage[c] = log((double)v);  // F:170
+            }
+            if (!good) bad.store(1);
+        };
+        if (use <= 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 1; t < use; ++t) pool.emplace_back(work, t);
+            work(0);
+            for (auto &th : pool) th.join();
+        }
+        FV_CUDA(cudaMemcpyAsync(m->LAd + (size_t)r0 * K, stage, (size_t)cells * sizeof(double), cudaMemcpyHostToDevice,
+                                ctx->stream));
+        FV_CUDA(cudaEventRecord(drained[nchunk & 1], ctx->stream));
     }
+    if (bad.load()) {
+        cudaStreamSynchronize(ctx->stream);
+        set_error("flashv_model_create: A/B/Pi entries must be finite and inside [0,1]");
+        return FLASHV_ERR_DOMAIN;
+    }
+
     std::vector<double> hLB((size_t)M * K), hLPi((size_t)K);
     std::vector<float> hLBf((size_t)M * Kp, 0.0f);
     for (int i = 0; i < K; ++i) {
@@ -129,49 +196,43 @@ int tables_build(flashv_model *m, const float *A, const float *B, const float *P
         }
         hLPi[i] = log((double)Pi[i]);  // F:142
     }
+    FV_CUDA(cudaMemcpyAsync(m->LBf, hLBf.data(), hLBf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    FV_CUDA(cudaMemcpyAsync(m->LBd, hLB.data(), hLB.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    FV_CUDA(cudaMemcpyAsync(m->LPi, hLPi.data(), hLPi.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    FV_CUDA(cudaStreamSynchronize(ctx->stream));  // the vectors are on this frame; the staging buffers are reusable
+    m->row_lo = row_lo, m->row_hi = row_hi;
+    m->prep_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return FLASHV_OK;
+}
 
-    cudaError_t e;
-#define TB_CUDA(call)                                                  \
-    if ((e = (call)) != cudaSuccess) {                                 \
-        cudaFreeHost(hLA);                                             \
-        return cuda_fail(e, #call, __FILE__, __LINE__);                \
-    }
-    TB_CUDA(cudaMalloc(&m->LAd, nA * sizeof(double)));
-    TB_CUDA(cudaMalloc(&m->hiT, (size_t)K * Kp * sizeof(float)));
-    TB_CUDA(cudaMalloc(&m->hiC, (size_t)K * Kp * sizeof(float)));
+// Every layout the kernels read is a re-arrangement of LAd and is built on the device.
+int tables_layouts(flashv_model *m)
+{
+    const int K = m->K, Kp = m->Kp;
+    flashv_ctx *ctx = m->ctx;
+    auto t0 = std::chrono::steady_clock::now();
+    FV_CUDA(cudaMalloc(&m->hiT, (size_t)K * Kp * sizeof(float)));
+    FV_CUDA(cudaMalloc(&m->hiC, (size_t)K * Kp * sizeof(float)));
+    m->bytes += (size_t)2 * K * Kp * 4;
     if (Kp <= GROUP_MAX_KP) {
-        TB_CUDA(cudaMalloc(&m->hiS, (size_t)Kp * Kp * sizeof(float)));
+        FV_CUDA(cudaMalloc(&m->hiS, (size_t)Kp * Kp * sizeof(float)));
         m->bytes += (size_t)Kp * Kp * sizeof(float);
     }
-    TB_CUDA(cudaMalloc(&m->LBf, (size_t)M * Kp * sizeof(float)));
-    TB_CUDA(cudaMalloc(&m->LBd, (size_t)M * K * sizeof(double)));
-    TB_CUDA(cudaMalloc(&m->LPi, (size_t)K * sizeof(double)));
-    TB_CUDA(cudaMalloc(&m->scratch_f, (size_t)4 * Kp * sizeof(float)));
-    TB_CUDA(cudaMalloc(&m->scratch_i, (size_t)2 * Kp * sizeof(int32_t)));
-    TB_CUDA(cudaMalloc(&m->scratch_x, (size_t)2 * Kp * 8));
-    m->bytes += nA * sizeof(double) + (size_t)2 * K * Kp * 4 + (size_t)M * Kp * 4 + (size_t)M * K * 8 + (size_t)K * 8 +
-               (size_t)6 * Kp * 4;
-    TB_CUDA(cudaMemcpyAsync(m->LAd, hLA, nA * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    TB_CUDA(cudaMemcpyAsync(m->LBf, hLBf.data(), hLBf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    TB_CUDA(cudaMemcpyAsync(m->LBd, hLB.data(), hLB.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    TB_CUDA(cudaMemcpyAsync(m->LPi, hLPi.data(), hLPi.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    TB_CUDA(cudaMemsetAsync(m->scratch_f, 0, (size_t)4 * Kp * sizeof(float), ctx->stream));
     dim3 grid((K + 31) / 32, (Kp + 31) / 32), block(32, 8);
     k_transpose_to_f32<<<grid, block, 0, ctx->stream>>>(m->LAd, m->hiT, K, Kp);
-    TB_CUDA(cudaGetLastError());
+    FV_CUDA(cudaGetLastError());
     if (m->hiS) {
         k_build_source_major<<<dim3((Kp + 255) / 256, Kp), 256, 0, ctx->stream>>>(m->LAd, m->hiS, K, Kp);
-        TB_CUDA(cudaGetLastError());
+        FV_CUDA(cudaGetLastError());
     }
     m->tile_G = ctx->sm_count < K ? ctx->sm_count : K;
     build_tiled_slice(m->LAd, m->hiC, K, Kp, 0, K, m->tile_G, ctx->stream);
-    TB_CUDA(cudaGetLastError());
-    TB_CUDA(cudaStreamSynchronize(ctx->stream));
-#undef TB_CUDA
-    const int sparse_rc = sparse_build(m, hLA);
-    cudaFreeHost(hLA);
-    if (sparse_rc != FLASHV_OK) return sparse_rc;
-    m->prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    FV_CUDA(cudaGetLastError());
+    const int rc = sparse_build(m);
+    if (rc != FLASHV_OK) return rc;
+    FV_CUDA(cudaStreamSynchronize(ctx->stream));
+    m->ready = true;
+    m->prep_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return FLASHV_OK;
 }
 

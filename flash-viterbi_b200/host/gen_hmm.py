@@ -32,10 +32,32 @@ def transition_matrix(K: int, prob: float, seed: int) -> np.ndarray:
     return A
 
 
+def transition_matrix_f32_into(out: np.ndarray, K: int, prob: float, seed: int) -> None:
+    """transition_matrix() followed by as_reference_floats(), written row by row into `out` ([K][K]
+    float32, e.g. a shared-memory mapping): the same numpy calls in the same order, hence the same
+    numbers, without ever holding the K x K float64 table (8.6 GB at K=32768).  Rows are independent
+    after the draws (normalisation is per row), so producing them one at a time changes nothing."""
+    np.random.seed(seed)
+    states = np.arange(K)  # choice() draws the same permutation for an array as for the reference's list
+    row = np.zeros(K)
+    for s in range(K):
+        fanout = np.random.binomial(K, p=prob, size=None)
+        targets = np.random.choice(states, size=fanout, replace=False)
+        row[:] = 0.0
+        row[targets] = np.random.uniform(0.01, 1, size=fanout)
+        out[s, :] = np.round(row / np.sum(row), 16).astype(np.float32)
+
+
 def emission_matrix(K: int, M: int, seed: int) -> np.ndarray:
     np.random.seed(seed)
     B = np.random.uniform(0.1, 1, (K, M))
     return B / B.sum(axis=1)[:, None]
+
+
+def observation_batch(count: int, T: int, M: int, first_seed: int, stride: int = 1) -> np.ndarray:
+    """`count` sequences of uniform symbols, sequence q seeded with first_seed + q*stride (numpy streams:
+    the per-call Python generator of observations() takes seconds for the 8192 x 1024 batches)."""
+    return np.stack([np.random.RandomState(first_seed + q * stride).randint(0, M, T) for q in range(count)]).astype(np.int32)
 
 
 def observations(T: int, M: int, ob_seed: int) -> np.ndarray:

@@ -34,7 +34,7 @@ parameters = [
 ]
 
 HEADER = ["timestamp", "K_STATE", "T_STATE", "obserRouteLEN", "prob", "MAX_THREADS", "BeamSearchWidth", "time", "memory"]
-EXTRA = ["score", "device_decode_ms", "model_prep_ms", "executed_steps", "device_bytes"]
+EXTRA = ["score", "device_decode_ms", "model_prep_ms", "time_including_prep", "executed_steps", "device_bytes"]
 
 
 def substitute(source: str, p: dict, data_path: str, program: str) -> str:

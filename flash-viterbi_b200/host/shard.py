@@ -7,7 +7,8 @@ import numpy as np
 
 
 def rank_sequences(total: int, world: int, rank: int) -> np.ndarray:
-    """Indices of the sequences rank `rank` decodes (b mod G == rank)."""
+    """Indices of the sequences rank `rank` decodes (b mod G == rank): the rows flashv_decode_batch_shard
+    fills in place; their number is flashv_shard_count(total, rank, world)."""
     return np.arange(rank, total, world, dtype=np.int64)
 
 

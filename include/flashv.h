@@ -35,11 +35,13 @@ typedef struct flashv_model flashv_model; /* device-resident log tables of one H
 typedef struct flashv_plan flashv_plan;   /* decode schedule + workspace for one (T, N, batch[, B]) */
 
 /* Which trellis engine the FLASH plan uses for single-vector passes (the N-way first pass and
- * the root task).  Both are exact; AUTO picks the persistent kernel when the device can hold
- * one CTA per SM co-resident. */
+ * the root task).  All are exact.  AUTO picks the persistent kernel when it fits the device
+ * (cooperative launch; delta vector + two ring stages in one CTA's shared memory: K up to ~42,000 on
+ * B200), else the per-step kernels.  Feasibility is decided by flashv_plan_create: FLASH plans accept
+ * K <= 56,320 (one delta vector in shared memory); a forced engine that does not fit is FLASHV_ERR_ARG. */
 #define FLASHV_ENGINE_AUTO 0
 #define FLASHV_ENGINE_STEP 1       /* one kernel launch per trellis step */
-#define FLASHV_ENGINE_PERSISTENT 2 /* one cooperative launch per pass, TMA-fed, grid barrier per step */
+#define FLASHV_ENGINE_PERSISTENT 2 /* one cooperative launch per pass, TMA-fed; steps hand over through tagged delta words, no grid barrier */
 #define FLASHV_ENGINE_SPARSE 3     /* opt-in: the pass walks the in-edge lists (entries with A[k][i] == 0 can never win,
                                       F:171), resident in shared memory; same results, not the dense roofline's bytes */
 
@@ -111,20 +113,70 @@ int flashv_plan_run(flashv_plan *plan);                                       /*
 int flashv_plan_download(flashv_plan *plan, int32_t *path_out, float *score_out); /* D2H + stream sync */
 int flashv_plan_report(flashv_plan *plan, flashv_report *report);            /* of the last run (syncs) */
 
+/* ---- model creation shared by the ranks of a box ------------------------------------------------ */
+/* What model creation costs is one host libm log() per table entry (F:170).  With `world` ranks on a
+ * box (one process per GPU) each rank computes the rows [rank*K/world, (rank+1)*K/world) only, and the
+ * rest arrives from the peers' device tables over NVLink:
+ *     flashv_model_create_rows(...)                 on every rank (A may be a shared mapping; only the
+ *                                                   rank's rows of it are read)
+ *     flashv_model_rows_handle(model, h)            64-byte cudaIpc handle; all-gather them; BARRIER
+ *     flashv_model_pull_rows(model, r, handle_r)    for every peer r (flashv_model_pull_rows_from inside
+ *                                                   one process, no handle)
+ *     BARRIER (peers may still be pulling from this rank's table) ; flashv_model_finish(model)
+ * The model decodes only after flashv_model_finish (layouts and edge lists are built on the device). */
+int flashv_model_create_rows(flashv_ctx *ctx, int K, int M, const float *A, const float *B, const float *Pi, int rank,
+                             int world, flashv_model **out);
+int flashv_model_rows_handle(flashv_model *model, void *out64);
+int flashv_model_pull_rows(flashv_model *model, int peer_rank, const void *handle64);
+int flashv_model_pull_rows_from(flashv_model *model, int peer_rank, const flashv_model *peer);
+int flashv_model_finish(flashv_model *model);
+
+/* ---- batches sharded over ranks (sequence b -> GPU b mod G, no data-path collective) --- */
+/* How many of `total` sequences rank `rank` of `world` decodes, and which: rank, rank+world, ... */
+int flashv_shard_count(int total, int rank, int world);
+/* Decode this rank's share of ob[total][T] and leave the rows in place in path_out[total][T] /
+ * score_out[total] (rows of other ranks are not touched): the caller gathers with whatever transport it
+ * has (MPI, torch.distributed, shared memory) — or uses flashv_mgpu_decode_batch inside one process. */
+int flashv_decode_batch_shard(flashv_model *model, const int32_t *ob, int total, int T, int N, int rank, int world,
+                              int32_t *path_out, float *score_out, flashv_report *report);
+
 /* ---- state sharding of one huge K across the GPUs of a box -------------------- */
 /* Every rank holds the full model and an identical FLASH plan (batch 1, persistent engine).  After
  * flashv_plan_shard_init(plan, rank, world) a rank computes only its slice of destination states
- * in the plan's first pass (the N-way pass of F:126-202, or the root task); each step it stores its slice
- * of delta and of the backpointer row into the buffers of ALL ranks with in-kernel peer stores over
- * NVLink and polls only its own copy — the per-step all-gather, with no host or NCCL call.  Everything
- * after that pass (the tree levels) runs replicated on every rank.  Ranks exchange their buffers once: raw pointers inside one process
- * (set_peer enables peer access), cudaIpc handles between processes (128 bytes per rank, e.g. through
- * torch.distributed.all_gather).  All ranks must call flashv_plan_run together (barrier first). */
+ * in the plan's pass 0 (the N-way pass of F:126-202, or the root task); each step it stores its slice
+ * of delta and of the backpointer row into the regions of ALL ranks with in-kernel peer stores over
+ * NVLink and polls only its own copy — the per-step all-gather, with no host or NCCL call.  The task
+ * tree that follows is spread over the ranks as well: rank r runs every world-th task of a level, and
+ * the level's Ans[] entries travel the same way (one tagged 64-bit word each) before the next level
+ * starts.  Ranks exchange their region once: the raw pointer inside one process (set_peer enables peer
+ * access), a 64-byte cudaIpc handle between processes (e.g. through torch.distributed.all_gather).
+ * CONTRACT: peers store into a plan's region during a run, so every rank must have COMPLETED run n
+ * (stream synchronised) before ANY rank calls flashv_plan_run for run n+1 — sync, barrier across ranks,
+ * run.  flashv_plan_run returns FLASHV_ERR_STATE if this rank's stream is still busy.  A rank whose peers
+ * do not show up within FLASHV_WATCHDOG_MS (default 30,000 across GPUs) traps instead of hanging. */
 int flashv_plan_shard_init(flashv_plan *plan, int rank, int world);
-int flashv_plan_shard_buffers(flashv_plan *plan, void **delta_base, void **psi_base);
-int flashv_plan_shard_ipc_handles(flashv_plan *plan, void *out128);
-int flashv_plan_shard_set_peer(flashv_plan *plan, int peer_rank, int peer_device, void *delta_base, void *psi_base);
-int flashv_plan_shard_open_peer(flashv_plan *plan, int peer_rank, const void *handles128);
+int flashv_plan_shard_buffers(flashv_plan *plan, void **region_base, size_t *region_bytes);
+int flashv_plan_shard_ipc_handle(flashv_plan *plan, void *out64);
+int flashv_plan_shard_set_peer(flashv_plan *plan, int peer_rank, int peer_device, void *region_base);
+int flashv_plan_shard_open_peer(flashv_plan *plan, int peer_rank, const void *handle64);
+
+/* ---- all GPUs of a box from ONE host process (what a C program like the reference's shell uses) ---- */
+/* A flashv_mgpu owns one context (and one host thread per call) per device.  The model is created once:
+ * every device's thread computes its share of the log tables and the shares are exchanged over NVLink. */
+typedef struct flashv_mgpu flashv_mgpu;
+int flashv_mgpu_create(int ndev, const int *devices /* NULL: 0..ndev-1 */, flashv_mgpu **out);
+void flashv_mgpu_destroy(flashv_mgpu *g);
+int flashv_mgpu_world(const flashv_mgpu *g);
+flashv_ctx *flashv_mgpu_ctx(flashv_mgpu *g, int rank);
+flashv_model *flashv_mgpu_model(flashv_mgpu *g, int rank);
+int flashv_mgpu_model_create(flashv_mgpu *g, int K, int M, const float *A, const float *B, const float *Pi);
+/* Batch of independent sequences: sequence b on device b mod G, paths gathered into path_out[batch][T].
+ * report: decode_ms = the slowest device's. */
+int flashv_mgpu_decode_batch(flashv_mgpu *g, const int32_t *ob, int batch, int T, int N, int32_t *path_out,
+                             float *score_out, flashv_report *report);
+/* One sequence over a K too large for one GPU to be fast: pass 0 state-sharded, tree levels spread (above). */
+int flashv_mgpu_decode(flashv_mgpu *g, const int32_t *ob, int T, int N, int32_t *path_out, float *score_out,
+                       flashv_report *report);
 
 /* ---- pieces of the pass, exposed for per-step parity tests ---------------------------- */
 /* Start vector of nvviter / nvviterNdivide (F:142, F:220): prev_state < 0 selects the pi form. */

@@ -97,6 +97,12 @@ STANDARD = [
     ("FLASH", 3965, 50, 34, 0.112, 16, None),
     ("FLASH_BS", 3965, 50, 34, 0.112, 8, 128),
     ("FLASH_BS", 3965, 50, 256, 0.112, 8, 128),
+    # bench.py --impl reference: the whole headline config at our segment count, and at the
+    # reference-comparable ones (a run is ~45 s on the GPU box's host: the N-way pass is single-threaded)
+    ("FLASH", 3965, 50, 256, 0.112, 127, None),
+    ("FLASH", 3965, 50, 256, 0.112, 8, None),
+    ("FLASH", 3965, 50, 256, 0.112, 64, None),
+    ("FLASH", 3965, 50, 256, 0.112, 1, None),
 ]
 
 

@@ -25,6 +25,16 @@
 
 struct fvo_model {
     int K, M;
+    /* lean form (fvo_model_create_lean, for shapes where two K x K double tables do not fit a host):
+     * per destination column the ascending list of sources k with A[k][i] > 0 and their logarithms.
+     * A source with A[k][i] == 0 has ktmp = -inf, which never passes "ktmp > score" from -FLT_MAX
+     * (F:167, F:171), so walking only the lists executes exactly the comparisons that can succeed, in
+     * the same order.  tests/test_oracle_golden.py checks lean == literal on every golden model. */
+    int lean;
+    const float *A; /* lean: borrowed, must outlive the model (start vectors read row Ans[L-1], F:220) */
+    long *cptr;     /* lean: [K+1] */
+    int *ck;        /* lean: [nnz] source state */
+    double *cla;    /* lean: [nnz] log((double)A[k][i]) */
     double *LA;   /* [k][i]  log((double)A[k][i])            F:170 */
     double *LAt;  /* [i][k]  same numbers, transposed so the k loop is unit stride */
     double *LB;   /* [i][o]  log((double)B[i][o])            F:142 */
@@ -65,9 +75,67 @@ fvo_model *fvo_model_create(int K, int M, const float *A, const float *B, const 
     return m;
 }
 
+fvo_model *fvo_model_create_lean(int K, int M, const float *A, const float *B, const float *Pi)
+{
+    fvo_model *m = (fvo_model *)calloc(1, sizeof(*m));
+    if (!m) return NULL;
+    m->K = K;
+    m->M = M;
+    m->lean = 1;
+    m->A = A;
+    m->cptr = (long *)calloc((size_t)K + 1, sizeof(long));
+    m->LB = (double *)malloc(sizeof(double) * (size_t)K * M);
+    m->LBf = (float *)malloc(sizeof(float) * (size_t)K * M);
+    m->LPi = (double *)malloc(sizeof(double) * (size_t)K);
+    if (!m->cptr || !m->LB || !m->LBf || !m->LPi) {
+        fvo_model_free(m);
+        return NULL;
+    }
+    /* every thread owns a range of columns: it reads that slice of every row, so its lists come out in
+     * ascending k without any coordination */
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < K; ++i) {
+        long c = 0;
+        for (int k = 0; k < K; ++k) c += A[(size_t)k * K + i] > 0.0f;
+        m->cptr[i + 1] = c;
+    }
+    for (int i = 0; i < K; ++i) m->cptr[i + 1] += m->cptr[i];
+    const long nnz = m->cptr[K];
+    m->ck = (int *)malloc(sizeof(int) * (size_t)(nnz ? nnz : 1));
+    m->cla = (double *)malloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
+    if (!m->ck || !m->cla) {
+        fvo_model_free(m);
+        return NULL;
+    }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < K; ++i) {
+        long e = m->cptr[i];
+        for (int k = 0; k < K; ++k) {
+            const float v = A[(size_t)k * K + i];
+            if (v > 0.0f) {
+                m->ck[e] = k;
+                m->cla[e] = log((double)v);
+                ++e;
+            }
+        }
+    }
+    for (int i = 0; i < K; ++i) {
+        for (int o = 0; o < M; ++o) {
+            double v = log((double)B[(size_t)i * M + o]);
+            m->LB[(size_t)i * M + o] = v;
+            m->LBf[(size_t)i * M + o] = (float)v;
+        }
+        m->LPi[i] = log((double)Pi[i]);
+    }
+    return m;
+}
+
 void fvo_model_free(fvo_model *m)
 {
     if (!m) return;
+    free(m->cptr);
+    free(m->ck);
+    free(m->cla);
     free(m->LA);
     free(m->LAt);
     free(m->LB);
@@ -84,7 +152,9 @@ void fvo_flash_init(const fvo_model *m, int prev_state, int o, float *d_out)
 {
     const int K = m->K, M = m->M;
     for (int i = 0; i < K; ++i) {
-        double head = prev_state < 0 ? m->LPi[i] : m->LA[(size_t)prev_state * K + i];
+        double head = prev_state < 0 ? m->LPi[i]
+                      : m->lean    ? log((double)m->A[(size_t)prev_state * K + i])
+                                   : m->LA[(size_t)prev_state * K + i];
         d_out[i] = (float)(head + m->LB[(size_t)i * M + o]);
     }
 }
@@ -95,6 +165,26 @@ void fvo_flash_init(const fvo_model *m, int prev_state, int o, float *d_out)
 void fvo_flash_step(const fvo_model *m, const float *d_in, int o, float *d_out, int *psi)
 {
     const int K = m->K, M = m->M;
+    if (m->lean) {
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int i = 0; i < K; ++i) {
+            const float tmp = m->LBf[(size_t)i * M + o];
+            float best = -FLT_MAX;
+            int arg = -1;
+            for (long e = m->cptr[i]; e < m->cptr[i + 1]; ++e) {
+                float pre = tmp + d_in[m->ck[e]];
+                double wide = (double)pre + m->cla[e];
+                float cand = (float)wide;
+                if (cand > best) {
+                    best = cand;
+                    arg = m->ck[e];
+                }
+            }
+            d_out[i] = best;
+            psi[i] = arg;
+        }
+        return;
+    }
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < K; ++i) {
         const double *col = m->LAt + (size_t)i * K;

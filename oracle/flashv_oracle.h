@@ -28,6 +28,12 @@ typedef struct fvo_model fvo_model;
  * libm log() tables once; log(x) of a given x is deterministic, so hoisting it out of the
  * inner loop (F:170) does not change a single bit. */
 fvo_model *fvo_model_create(int K, int M, const float *A, const float *B, const float *Pi);
+/* The same model for FLASH decodes of shapes whose K x K double tables do not fit the host (K=32768:
+ * 2 x 8.6 GB): only the entries with A[k][i] > 0 are kept, as ascending per-column lists.  A zero entry
+ * gives ktmp = -inf, which never passes the strict '>' from -FLT_MAX (F:167, F:171), so the decode is the
+ * same function; checked against the literal form on the golden models.  A is BORROWED (start vectors
+ * read it, F:220) and must outlive the model.  FLASH only: the fvo_bs_* entry points need the full form. */
+fvo_model *fvo_model_create_lean(int K, int M, const float *A, const float *B, const float *Pi);
 void fvo_model_free(fvo_model *m);
 
 /* calc() of F:338-368 for one observation sequence.  path[T]; *score = max_i delta_{T-1}[i] of

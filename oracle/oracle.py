@@ -36,6 +36,8 @@ def lib():
         fp, ip, vp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_void_p
         L.fvo_model_create.restype = vp
         L.fvo_model_create.argtypes = [C.c_int, C.c_int, fp, fp, fp]
+        L.fvo_model_create_lean.restype = vp
+        L.fvo_model_create_lean.argtypes = [C.c_int, C.c_int, fp, fp, fp]
         L.fvo_model_free.argtypes = [vp]
         L.fvo_flash_decode.argtypes = [vp, ip, C.c_int, C.c_int, ip, fp, ip]
         L.fvo_bs_decode.argtypes = [vp, ip, C.c_int, C.c_int, C.c_int, ip, fp, ip]
@@ -67,13 +69,17 @@ def _i(a):
 class OracleModel:
     """HMM held the way the reference's VIT struct holds it (float32 A, B, Pi)."""
 
-    def __init__(self, A, B, Pi):
+    def __init__(self, A, B, Pi, lean=False):
+        """lean=True keeps only the non-zero transitions (fvo_model_create_lean): FLASH decodes only,
+        for shapes like K=32768 whose dense double tables would not fit the host."""
         self.A = np.ascontiguousarray(A, dtype=np.float32)
         self.B = np.ascontiguousarray(B, dtype=np.float32)
         self.Pi = np.ascontiguousarray(Pi, dtype=np.float32)
         self.K, self.M = self.B.shape
+        self.lean = bool(lean)
         assert self.A.shape == (self.K, self.K) and self.Pi.shape == (self.K,)
-        self._h = lib().fvo_model_create(self.K, self.M, _f(self.A), _f(self.B), _f(self.Pi))
+        create = lib().fvo_model_create_lean if lean else lib().fvo_model_create
+        self._h = create(self.K, self.M, _f(self.A), _f(self.B), _f(self.Pi))
         if not self._h:
             raise MemoryError("fvo_model_create")
 
@@ -93,6 +99,7 @@ class OracleModel:
         return path, np.float32(score.value), mem.value
 
     def flash_bs(self, ob, N, Bw):
+        assert not self.lean, "the lean oracle model decodes FLASH only"
         ob = np.ascontiguousarray(ob, dtype=np.int32)
         T = ob.shape[0]
         path = np.empty(T, np.int32)
@@ -168,3 +175,11 @@ def read_ints(path, n):
     if got != n:
         raise IOError(f"{path}: wanted {n} ints, got {got}")
     return out
+
+
+def set_threads(n: int) -> None:
+    """OpenMP threads of the oracle's loops (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass

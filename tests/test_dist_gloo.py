@@ -42,6 +42,12 @@ def test_sequences_shard_over_two_ranks():
 
     assert list(shard.rank_sequences(7, 2, 0)) == [0, 2, 4, 6] and list(shard.rank_sequences(7, 2, 1)) == [1, 3, 5]
     assert sorted(np.concatenate([shard.rank_sequences(9, 4, r) for r in range(4)])) == list(range(9))
+    from conftest import load_pkg
+
+    fv = load_pkg()  # the C ABI's count is the length of that index list (pure host function: runs without a GPU)
+    for total, world in ((7, 2), (9, 4), (3, 8), (8192, 8), (0, 3)):
+        for r in range(world):
+            assert fv.shard_count(total, r, world) == len(shard.rank_sequences(total, world, r))
     g = load_golden("hmm_k37")
     rng = np.random.RandomState(5)
     obs = rng.randint(0, g["B"].shape[1], (5, 40)).astype(np.int32)

@@ -393,51 +393,6 @@ def test_wide_model_multi_round(fv, oracle_mod, gpu_ctx):
     model.close()
 
 
-def _device_count():
-    import torch
-
-    return torch.cuda.device_count()
-
-
-@pytest.mark.parametrize("K,T,N,world", [(300, 40, 4, 2), (3965, 24, 3, 2), (8200, 10, 2, 2), (1000, 30, 1, 4)])
-def test_state_sharded_first_pass(fv, oracle_mod, K, T, N, world):
-    """destination states sharded over `world` GPUs, per-step delta exchange with in-kernel
-    peer stores.  One process drives all GPUs here; every rank must end with the reference's path."""
-    if _device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
-    A, B, Pi = random_hmm(K, 6, 0.01 if K > 5000 else (0.05 if K > 2000 else 0.2), 81)
-    om = oracle_mod.OracleModel(A, B, Pi)
-    ob = np.random.RandomState(81).randint(0, 6, T).astype(np.int32)
-    want, wscore, _ = om.flash(ob, N)
-    ctxs = [fv.Context(r) for r in range(world)]
-    models = [fv.Model(c, A, B, Pi) for c in ctxs]
-    plans = [fv.Plan(m, T, N, 1, 0, fv.ENGINE_PERSISTENT) for m in models]
-    for r, p in enumerate(plans):
-        p.shard_init(r, world)
-    bufs = [p.shard_buffers() for p in plans]
-    for r, p in enumerate(plans):
-        for q in range(world):
-            if q != r:
-                p.shard_set_peer(q, q, bufs[q][0], bufs[q][1])
-    for rep in range(2):  # twice: the epoch tags must keep runs apart
-        for p in plans:
-            p.upload(ob)
-        for c in ctxs:
-            c.sync()
-        for p in plans:
-            p.run()  # asynchronous: the ranks' kernels wait for each other's slices
-        for r, p in enumerate(plans):
-            paths, scores = p.download()
-            assert np.array_equal(paths[0], want), (rep, r, np.nonzero(paths[0] != want)[0][:6])
-            assert _bits(scores[0]) == _bits(wscore)
-    for p in plans:
-        p.close()
-    for m in models:
-        m.close()
-    for c in ctxs:
-        c.close()
-
-
 def test_error_behaviour(fv, gpu_ctx):
     A, B, Pi = random_hmm(16, 4, 0.5, 51)
     model = fv.Model(gpu_ctx, A, B, Pi)

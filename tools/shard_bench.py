@@ -62,7 +62,7 @@ def main():
         for r, p in enumerate(plans):
             for q in range(world):
                 if q != r:
-                    p.shard_set_peer(q, q, bufs[q][0], bufs[q][1])
+                    p.shard_set_peer(q, q, bufs[q][0])
         best = None
         for it in range(a.iters + 1):
             for p in plans:
