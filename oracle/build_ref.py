@@ -103,6 +103,9 @@ STANDARD = [
     ("FLASH", 3965, 50, 256, 0.112, 8, None),
     ("FLASH", 3965, 50, 256, 0.112, 64, None),
     ("FLASH", 3965, 50, 256, 0.112, 1, None),
+    # tests/test_host_programs.py::test_host_programs_read_dag_named_files
+    ("FLASH", 96, 50, 64, 0.9, 9, None),
+    ("FLASH_BS", 96, 50, 64, 0.9, 4, 16),
 ]
 
 

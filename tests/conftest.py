@@ -46,7 +46,8 @@ def oracle_mod():
     return oracle
 
 
-GOLDEN_NAMES = ["hmm_k64", "hmm_k37", "hmm_k128", "hmm_k257"]
+# dag_k96: a DAG-structured HMM in data_script_dag.py's construction (tests/golden/make_golden_dag.py)
+GOLDEN_NAMES = ["hmm_k64", "hmm_k37", "hmm_k128", "hmm_k257", "dag_k96"]
 
 
 def load_golden(name):

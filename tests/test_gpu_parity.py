@@ -457,3 +457,61 @@ def test_headline_flash_bs_vs_oracle(fv, headline):
         got, score, rep = model.bs_decode(ob, N, Bw)
         assert np.array_equal(got, want), (N, Bw)
         assert _bits(score) == _bits(wscore) and rep.memory_bytes == wmem
+
+
+@pytest.fixture(scope="module")
+def bench_instance(fv, oracle_mod, gpu_ctx):
+    """The exact instance bench.py times: gen_hmm.make_hmm(3965, 50, 0.112, 1) — the numbers of
+    `data_script.py -s 1` — and the observation sequence of seed 1000."""
+    import sys
+
+    from conftest import ROOT
+
+    sys.path.insert(0, str(ROOT / "flash-viterbi_b200" / "host"))
+    import gen_hmm
+
+    A, B, Pi = gen_hmm.make_hmm(3965, 50, 0.112, 1)
+    f = gen_hmm.as_reference_floats
+    A, B, Pi = f(A), f(B), f(Pi)
+    ob = gen_hmm.observations(256, 50, 1000)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    yield model, A, B, Pi, ob
+    model.close()
+
+
+@pytest.mark.parametrize("N", [127, 1, 2, 8])
+def test_bench_instance_flash(fv, oracle_mod, bench_instance, N):
+    """bench.py's default segment count (127), the reference driver's own (src/run.py:14: 1), the largest
+    N without an N-way pass (2) and the reference-comparable 8, on the bench's own model and sequence."""
+    model, A, B, Pi, ob = bench_instance
+    om = oracle_mod.OracleModel(A, B, Pi, lean=True)
+    want, wscore, wmem = om.flash(ob, N)
+    for eng in (fv.ENGINE_AUTO, fv.ENGINE_STEP, fv.ENGINE_SPARSE):
+        plan = fv.Plan(model, len(ob), N, 1, 0, eng)
+        plan.upload(ob)
+        plan.run()
+        paths, scores = plan.download()
+        rep = plan.report()
+        plan.close()
+        assert np.array_equal(paths[0], want), (N, eng)
+        assert _bits(scores[0]) == _bits(wscore) and rep.memory_bytes == wmem
+    path, score, _ = model.decode(ob, N)  # the one-call form bench.py's e2e leg times
+    assert np.array_equal(path, want) and _bits(score) == _bits(wscore)
+
+
+@pytest.mark.parametrize("N,Bw,ob_seed,dropouts", [(127, 128, 1000, False), (8, 128, 1000, False), (1, 32, 1000, False),
+                                                    (1, 32, 1002, True), (8, 32, 1002, True), (1, 8, 1000, True)])
+def test_bench_instance_flash_bs(fv, oracle_mod, bench_instance, N, Bw, ob_seed, dropouts):
+    """FLASH-BS as bench.py times it (N=127 and 8 at B=128) and in the reference driver's own setting
+    (src/run.py:10-16: N=1, B=32).  With the sequence of seed 1002 (and at B=8) states fall out of the beam
+    and leave -1 entries in the path (7 of 256 on the survey's own unseeded sequence)."""
+    import gen_hmm
+
+    model, A, B, Pi, _ = bench_instance
+    ob = gen_hmm.observations(256, 50, ob_seed)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    want, wscore, wmem = om.flash_bs(ob, N, Bw)
+    got, score, rep = model.bs_decode(ob, N, Bw)
+    assert np.array_equal(got, want), (N, Bw, np.nonzero(got != want)[0][:8])
+    assert _bits(score) == _bits(wscore) and rep.memory_bytes == wmem
+    assert ((want < 0).sum() > 0) == dropouts

@@ -77,3 +77,43 @@ def test_host_program_matches_reference_binary(fv, tmp_path):
         row = [c for c in range(len(g["case_prog"])) if g["case_prog"][c] == (0 if B is None else 1)
                and g["case_seq"][c] == 0 and g["case_N"][c] == 8 and g["case_B"][c] == (B or 0)][0]
         assert pick(ours.stdout, "path:") == "path: [" + "".join(f"{x} " for x in g["case_path"][row]) + "]"
+
+
+@pytest.mark.gpu
+def test_host_programs_read_dag_named_files(fv, tmp_path):
+    """files named as generate_data/data_script_dag.py names them (`*_K{K}_T{T}_DAG.txt`, DD:63-66).
+    The reference programs cannot open those names (F:51); ours fall back to them.  Same text the golden
+    run decoded (tests/golden/make_golden_dag.py), so the path must equal what the UNMODIFIED reference
+    printed for the `prob`-named copies — and, where its binary travelled along, what it prints now."""
+    import shutil
+
+    import run as host_run
+    from oracle import build_ref
+
+    g = load_golden("dag_k96")
+    K, M, T = 96, 50, 64
+    data = tmp_path / "data"
+    data.mkdir()
+    np.savetxt(data / f"A_K{K}_T{T}_DAG.txt", g["A64"], fmt="%.16f")
+    np.savetxt(data / f"B_K{K}_T{T}_DAG.txt", g["B64"], fmt="%.16f")
+    np.savetxt(data / f"Pi_K{K}_T{T}_DAG.txt", g["Pi64"], fmt="%.16f", newline=" ")
+    np.savetxt(data / f"ob_K{K}_T{T}_DAG.txt", g["obs"][0], fmt="%d", newline=" ")
+    pick = lambda out, key: [ln for ln in out.splitlines() if ln.startswith(key)][0]
+    for program, prog, N, B in (("FLASH_Viterbi_multithread", "FLASH", 9, None), ("FLASH_BS_Viterbi_multithread", "FLASH_BS", 4, 16)):
+        p = {"K_STATE": K, "T_STATE": M, "obserRouteLEN": T, "prob": 0.9, "MAX_THREADS": N, "BeamSearchWidth": B or 8}
+        binary = host_run.compile_program(program, p, "./data/", tmp_path / "build")
+        ours = subprocess.run([str(binary)], cwd=tmp_path, capture_output=True, text=True)
+        assert ours.returncode == 0, ours.stderr
+        row = [c for c in range(len(g["case_prog"])) if g["case_prog"][c] == (0 if B is None else 1)
+               and g["case_N"][c] == N and g["case_B"][c] == (B or 0)][0]
+        assert pick(ours.stdout, "path:") == "path: [" + "".join(f"{x} " for x in g["case_path"][row]) + "]"
+        assert pick(ours.stdout, "memory:") == f"memory: {g['case_memory'][row]}"
+        ref_bin = build_ref.OUT_DIR / build_ref.binary_name(prog, K, M, T, 0.9, N, B)
+        if ref_bin.exists():
+            for kind in ("A", "B", "Pi", "ob"):
+                shutil.copy(data / f"{kind}_K{K}_T{T}_DAG.txt", build_ref.data_file(data, kind, K, T, 0.9))
+            ref = subprocess.run([str(ref_bin)], cwd=tmp_path, capture_output=True, text=True)
+            assert ref.returncode == 0
+            assert pick(ours.stdout, "path:") == pick(ref.stdout, "path:")
+            for kind in ("A", "B", "Pi", "ob"):  # the next program must find the _DAG names only
+                build_ref.data_file(data, kind, K, T, 0.9).unlink()
