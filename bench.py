@@ -120,6 +120,7 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "5"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)  # nvidia-smi needs a moment before its first sample; the timed regions are short
         except Exception:
             self.proc = None
 

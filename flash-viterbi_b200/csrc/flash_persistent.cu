@@ -24,6 +24,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "flashv_internal.h"
@@ -154,6 +155,30 @@ __device__ __forceinline__ float4 tmem_ld4(uint32_t taddr)
     return make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z), __uint_as_float(w));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 consecutive tensor-memory columns of this thread's lane in ONE instruction: four 128-state iterations of
+// both columns a warp owns (layout below: columns 8u..8u+3 first column, 8u+4..8u+7 second).  A tcgen05.ld
+// costs the tensor-memory read path a fixed ~8 cycles plus its bytes at ~54 B/clk (measured: 448 .x4 loads
+// per step took 4.0 us = 17.5 cycles each, 112 .x16 loads 46 cycles each), so the narrow form that fetched
+// one float4 per instruction spent a third of the phase on per-instruction cost.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float4 (&ha)[4], float4 (&hb)[4])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        ha[e] = make_float4(__uint_as_float(r[8 * e]), __uint_as_float(r[8 * e + 1]), __uint_as_float(r[8 * e + 2]), __uint_as_float(r[8 * e + 3]));
+        hb[e] = make_float4(__uint_as_float(r[8 * e + 4]), __uint_as_float(r[8 * e + 5]), __uint_as_float(r[8 * e + 6]), __uint_as_float(r[8 * e + 7]));
+    }
+}
 
 struct PersistArgs {
     const float *hiC;  // CTA-tiled (float)log A of the columns [col_begin, col_begin+ncol), tile_geom.h
@@ -175,6 +200,7 @@ struct PersistArgs {
     void *psi;
     int psi16;
     int nstage;
+    int pinned;  // 1: the streamed part of every CTA's slice fits the ring whole — it is loaded once and never refilled
     int l2_hint;
     unsigned long long watchdog_ns;  // how long a poll for delta words may last before the kernel traps (longer across GPUs)
     long long *trace;  // optional [TRACE_STEPS][grid][2 warps][TRACE_PTS] clock64 samples (FLASHV_TRACE_FILE), else null
@@ -425,7 +451,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
 
     if (warp == NCW) {
         // ---------------- producer: the slab, once per step, linearly through the ring -----------
-        if (lane == 0) {
+        if (lane == 0 && a.pinned) {
+            // the whole streamed part fits: one copy per chunk, packed back to back exactly as the table stores
+            // them (the last chunk may be shorter), each with its own barrier; nothing is ever refilled
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(slab) + (size_t)nk_res * TILE_CH * ncols * sizeof(float);
+            size_t off = 0;
+            for (int u = nk_res; u < nk; ++u) {
+                const uint32_t bytes = (uint32_t)(ncols * min(TILE_CH, a.Kp - u * TILE_CH)) * 4u;
+                mbar_expect_tx(&full[u - nk_res], bytes);
+                bulk_g2s(ring + off, src + off, bytes, &full[u - nk_res], 0, false);
+                off += bytes;
+            }
+        } else if (lane == 0) {
             const uint64_t pol = policy_evict_last();
             int st = 0;
             uint32_t use = 0;  // how often the ring has wrapped: stage st is being filled for the use-th time
@@ -520,12 +557,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
 #pragma unroll
                         for (int u = 0; u < TM_RES_CHUNKS * (TILE_CH / 128); u += 4) {
                             float4 ha[4], hb[4], dd[4];
+                            tmem_ld32(tbase + 8u * (uint32_t)u, ha, hb);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                ha[e] = tmem_ld4(tbase + 8u * (uint32_t)(u + e));
-                                hb[e] = tmem_ld4(tbase + 8u * (uint32_t)(u + e) + 4u);
-                                dd[e] = d4[(u + e) * 32];
-                            }
+                            for (int e = 0; e < 4; ++e) dd[e] = d4[(u + e) * 32];
                             tmem_wait_ld();
 #pragma unroll
                             for (int e = 0; e < 4; ++e) { FV_ACC2(dd[e], ha[e], hb[e]) }
@@ -543,8 +577,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                 }
                 } else if (TM || ph == 0) {
                     for (int u = nk_res; u < nk; ++u) {
-                    const float4 *stage4 = reinterpret_cast<const float4 *>(ring + (size_t)st * STAGE_BYTES);
-                    mbar_wait(&full[st], parity);
+                    const float4 *stage4 = reinterpret_cast<const float4 *>(
+                        a.pinned ? ring + (size_t)(u - nk_res) * ncr * TILE_CH * sizeof(float) : ring + (size_t)st * STAGE_BYTES);
+                    if (!a.pinned) mbar_wait(&full[st], parity);
+                    else if (s == 1) mbar_wait(&full[u - nk_res], 0);
                     if (have0) {
                         if (u < nk_full) {
 #pragma unroll
@@ -567,9 +603,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                         }
                     }
                     dring += TILE_CH >> 2;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[st]);
-                    if (++st == a.nstage) st = 0, parity ^= 1;
+                    if (!a.pinned) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[st]);
+                        if (++st == a.nstage) st = 0, parity ^= 1;
+                    }
                 }
                 }
             }
@@ -633,299 +671,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
     }
 }
 
-// ---- the whole table slice on chip ---------------------------------------------------------------
-// k_flash_resident: the same pass for models small enough that a CTA's slice of the float table
-// (~27 columns x Kp floats, 428 KB at K=3965 on 148 SMs) fits the SM's on-chip memories TOGETHER:
-// source states [0, S) of every owned column live in tensor memory (S <= 2048: 4 columns x 2048 x 4 B
-// per warp, 224 KB), states [S, Kp) in shared memory (207 KB at K=3965).  Both are loaded once; after
-// that a step reads no table byte from L2 — the ring, its TMA refill traffic (which cost as much
-// shared-memory bandwidth as the reads themselves) and the per-stage mbarrier traffic are gone, and
-// so is the L2 round trip of the window scan: the winning chain is re-read from the on-chip copy.
-//
-// Work split: warp pair p (warps p and p+RP) owns the four columns 4p..4p+3 of the CTA.  Warp p
-// sweeps the tensor-memory half of the source axis for all four (64 B/clk read path), warp p+RP the
-// shared-memory half (128 B/clk) — both pipes busy for the whole phase, every delta value read meets
-// four columns (half the shared-memory delta traffic of the two-column layout).  The halves meet in
-// shared memory twice: once for the column maxima (window threshold), once for the exact results.
-constexpr int RP = 7;                 // warp pairs
-constexpr int RCOLS = 4;              // columns per pair
-constexpr int RES_MAX_COLS = RP * RCOLS;
-static_assert(RES_MAX_COLS == TILE_RW, "the resident kernel uses the tiling of the ring kernel (one round of TILE_RW columns)");
-constexpr int RES_TM_STATES = 2048;   // 4 columns x 2048 states x 4 B = 256 tensor-memory columns per warp
-
-struct PairSlot {  // what the two warps of a pair hand each other, per column
-    float top[2][RCOLS];
-    float bx[2][RCOLS];
-    int bk[2][RCOLS];
-};
-
-// One candidate chain of a tensor-memory warp: the 16 elements k = 4*(w+32u)+c of column j sit in TMEM
-// lane w, so lane w walks them alone (every lane executes the loads; only lane w's values matter).
-template <int NU>
-__device__ __forceinline__ void rescan_tmem(Pending &p, uint32_t tbase, int j, int w, int c, int nu, float tmp, int thr,
-                                            const float *sdelta, const double *__restrict__ LAd, int K, int i, int lane)
-{
-    float v[NU];
-#pragma unroll
-    for (int u = 0; u < NU; ++u) {
-        uint32_t x;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(x) : "r"(tbase + 16u * (uint32_t)u + 4u * (uint32_t)j + (uint32_t)c) : "memory");
-        v[u] = __uint_as_float(x);
-    }
-    tmem_wait_ld();
-    if (lane == w) {
-#pragma unroll
-        for (int u = 0; u < NU; ++u)
-            if (u < nu) {
-                const int k = 4 * (w + 32 * u) + c;
-                if (k < K) {
-                    const float pre = __fadd_rn(tmp, sdelta[k]);
-                    if (ford(__fadd_rn(pre, v[u])) >= thr) pending_push(p, pre, k, LAd + (size_t)k * K + i);
-                }
-            }
-    }
-}
-
-__global__ void __launch_bounds__(NTHREADS, 1) k_flash_resident(const PersistArgs a, int S)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int Kp4 = a.Kp >> 2;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(full + 2 * MAX_STAGES);
-    float4 *sdelta4 = reinterpret_cast<float4 *>(smem_raw + CTRL_BYTES);
-    PairSlot *spair = reinterpret_cast<PairSlot *>(sdelta4 + Kp4);
-    float *srest = reinterpret_cast<float *>(spair + RP);  // [chunk][row][state] exactly as the tiled table stores it
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x, b = blockIdx.x;
-    const int c0 = tile_c0(a.ncol, G, b), ncols = tile_c0(a.ncol, G, b + 1) - c0;  // <= RES_MAX_COLS: one round
-    const float *slab = a.hiC + (size_t)c0 * a.Kp;
-    const int rest_states = a.Kp - S;
-
-    if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_fence_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_slot);
-    tmem_fence_before();
-    __syncthreads();
-    tmem_fence_after();
-
-    if (warp == 2 * RP) {
-        // loader: the shared-memory half of the slice, once; the copy engine runs while the other warps
-        // park their half in tensor memory
-        if (lane == 0 && rest_states > 0) {
-            const uint32_t total = (uint32_t)rest_states * (uint32_t)ncols * 4u;
-            mbar_expect_tx(&full[0], total);
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(slab) + (size_t)S * ncols * 4;
-            unsigned char *dst = reinterpret_cast<unsigned char *>(srest);
-            for (uint32_t off = 0; off < total; off += 32768u) {
-                const uint32_t n = total - off < 32768u ? total - off : 32768u;
-                bulk_g2s(dst + off, src + off, n, &full[0], 0, false);
-            }
-        }
-        return;
-    }
-
-    // ---------------- consumers: warps 0..RP-1 tensor-memory half, RP..2RP-1 shared-memory half ------
-    const bool tm_half = warp < RP;
-    const int pair = tm_half ? warp : warp - RP, half = tm_half ? 0 : 1;
-    const float *sdelta = reinterpret_cast<const float *>(sdelta4);
-    const uint32_t tbase = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + 256u * (uint32_t)(warp >> 2);
-    const int nu_t = S >> 7;            // 128-state iterations of the tensor-memory half (<= 16)
-    const int nu_s = rest_states >> 7;  // ... of the shared-memory half
-    int rr[RCOLS];                      // rows (local columns) of this pair; a missing one is a duplicate of the pair's first
-    bool have[RCOLS];
-#pragma unroll
-    for (int j = 0; j < RCOLS; ++j) {
-        have[j] = pair * RCOLS + j < ncols;
-        rr[j] = have[j] ? pair * RCOLS + j : (pair * RCOLS < ncols ? pair * RCOLS : 0);
-    }
-    const bool pair_live = pair * RCOLS < ncols;  // warp-uniform
-    if (tm_half && pair_live) {
-        for (int u = 0; u < nu_t; ++u) {
-            const int k = 4 * (lane + 32 * u);
-#pragma unroll
-            for (int j = 0; j < RCOLS; ++j)
-                tmem_st4(tbase + 16u * (uint32_t)u + 4u * (uint32_t)j,
-                         __ldg(reinterpret_cast<const float4 *>(slab + tile_round_off(a.Kp, ncols, rr[j], k))));
-        }
-        tmem_wait_st();
-    }
-    tmem_fence_before();
-    named_bar_sync(1, NCONS);
-    tmem_fence_after();
-    if (rest_states > 0) mbar_wait(&full[0], 0);
-
-    // address of (row, state k >= S) in srest: chunks of TILE_CH states, the last one possibly shorter
-    auto rest_ptr = [&](int row, int k) -> const float * {
-        const int kr = k - S, cu = kr / TILE_CH, len = min(TILE_CH, rest_states - cu * TILE_CH);
-        return srest + (size_t)cu * TILE_CH * ncols + (size_t)row * len + (kr - cu * TILE_CH);
-    };
-
-    for (int s = 1; s <= a.nsteps; ++s) {
-        unsigned long long *xout = a.xch + (size_t)(s & 1) * a.Kp;
-        const bool last_step = s == a.nsteps;
-        const int jstep = a.L + s;
-        const float *tmp_row = a.LBf + (size_t)__ldg(a.ob + jstep) * a.Kp;  // F:167
-        const bool keep = jstep >= a.mid + 1;                                // F:242
-        const bool tracing = a.trace != nullptr && s <= TRACE_STEPS && lane == 0 && (warp == 0 || warp == 2 * RP - 1);
-        long long *tr = tracing ? a.trace + ((((size_t)(s - 1) * G + b) * 2 + (warp == 0 ? 0 : 1)) * TRACE_PTS) : nullptr;
-        if (tracing) tr[0] = clock64();
-        delta_wait_load(a, s, reinterpret_cast<float *>(sdelta4), tid);
-        if (tracing) tr[1] = clock64();
-        if (!pair_live) {  // warp-uniform: this pair owns no column of the CTA (only when ncols < 4*RP - 3)
-            named_bar_sync(1, NCONS);
-            continue;
-        }
-        int icol[RCOLS];
-        float tmp[RCOLS];
-        float cm[RCOLS][4];
-#pragma unroll
-        for (int j = 0; j < RCOLS; ++j) {
-            icol[j] = a.col_begin + c0 + rr[j];
-            tmp[j] = __ldg(tmp_row + icol[j]);
-            cm[j][0] = cm[j][1] = cm[j][2] = cm[j][3] = -INFINITY;
-        }
-#define FV_ACC4(D, H)                                                                    \
-    _Pragma("unroll") for (int j = 0; j < RCOLS; ++j) {                                  \
-        cm[j][0] = fmaxf(cm[j][0], __fadd_rn(__fadd_rn(tmp[j], (D).x), (H)[j].x));        \
-        cm[j][1] = fmaxf(cm[j][1], __fadd_rn(__fadd_rn(tmp[j], (D).y), (H)[j].y));        \
-        cm[j][2] = fmaxf(cm[j][2], __fadd_rn(__fadd_rn(tmp[j], (D).z), (H)[j].z));        \
-        cm[j][3] = fmaxf(cm[j][3], __fadd_rn(__fadd_rn(tmp[j], (D).w), (H)[j].w));        \
-    }
-        if (tm_half) {
-            const float4 *d4 = sdelta4 + lane;
-            if (nu_t == RES_TM_STATES / 128) {
-#pragma unroll
-                for (int u = 0; u < RES_TM_STATES / 128; u += 2) {  // two iterations per tcgen05.wait: eight loads in flight
-                    float4 h0[RCOLS], h1[RCOLS];
-#pragma unroll
-                    for (int j = 0; j < RCOLS; ++j) {
-                        h0[j] = tmem_ld4(tbase + 16u * (uint32_t)u + 4u * (uint32_t)j);
-                        h1[j] = tmem_ld4(tbase + 16u * (uint32_t)(u + 1) + 4u * (uint32_t)j);
-                    }
-                    const float4 da = d4[u * 32], db = d4[(u + 1) * 32];
-                    tmem_wait_ld();
-                    FV_ACC4(da, h0)
-                    FV_ACC4(db, h1)
-                }
-            } else {
-                for (int u = 0; u < nu_t; ++u) {
-                    float4 h0[RCOLS];
-#pragma unroll
-                    for (int j = 0; j < RCOLS; ++j) h0[j] = tmem_ld4(tbase + 16u * (uint32_t)u + 4u * (uint32_t)j);
-                    const float4 da = d4[u * 32];
-                    tmem_wait_ld();
-                    FV_ACC4(da, h0)
-                }
-            }
-        } else {
-            const float4 *d4 = sdelta4 + (S >> 2) + lane;
-            const float4 *r4 = reinterpret_cast<const float4 *>(srest);
-            const int nfull = rest_states / TILE_CH;  // whole chunks; at most one shorter chunk (128 states... any multiple of 128) follows
-            for (int cu = 0; cu < nfull; ++cu) {
-                const float4 *ch = r4 + (size_t)cu * (TILE_CH >> 2) * ncols + lane;
-#pragma unroll
-                for (int it = 0; it < TILE_CH / 128; ++it) {
-                    float4 h0[RCOLS];
-#pragma unroll
-                    for (int j = 0; j < RCOLS; ++j) h0[j] = ch[rr[j] * (TILE_CH >> 2) + it * 32];
-                    const float4 da = d4[(cu * (TILE_CH / 128) + it) * 32];
-                    FV_ACC4(da, h0)
-                }
-            }
-            const int tail = rest_states - nfull * TILE_CH;  // states of the short last chunk
-            if (tail > 0) {
-                const float4 *ch = r4 + (size_t)nfull * (TILE_CH >> 2) * ncols + lane;
-                const int len4 = tail >> 2;
-                for (int it = 0; it < tail / 128; ++it) {
-                    float4 h0[RCOLS];
-#pragma unroll
-                    for (int j = 0; j < RCOLS; ++j) h0[j] = ch[rr[j] * len4 + it * 32];
-                    const float4 da = d4[(nfull * (TILE_CH / 128) + it) * 32];
-                    FV_ACC4(da, h0)
-                }
-            }
-        }
-#undef FV_ACC4
-        if (tracing) tr[2] = clock64();
-
-        // ---- column maxima of both halves -> window thresholds --------------------------------------
-        PairSlot &ps = spair[pair];
-#pragma unroll
-        for (int j = 0; j < RCOLS; ++j) {
-            const float t = warp_max(fmaxf(fmaxf(cm[j][0], cm[j][1]), fmaxf(cm[j][2], cm[j][3])));
-            if (lane == 0) ps.top[half][j] = t;
-        }
-        named_bar_sync(2 + pair, 64);
-        int thr[RCOLS];
-        bool dead[RCOLS];
-#pragma unroll
-        for (int j = 0; j < RCOLS; ++j) {
-            const float top = fmaxf(ps.top[0][j], ps.top[1][j]);
-            dead[j] = !(top > -FLT_MAX);
-            thr[j] = ford(top) - WINDOW_STEPS;
-        }
-        // ---- chains inside the window: re-read them from the on-chip copy, start the exact loads -----
-        Pending q[RCOLS];
-#pragma unroll
-        for (int j = 0; j < RCOLS; ++j) {
-            q[j].acc = Best{-FLT_MAX, 0x7fffffff};
-            q[j].has = false, q[j].la = 0.0, q[j].pre = 0.f, q[j].k = 0;
-            if (dead[j] || !have[j]) continue;  // warp-uniform
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                unsigned hit = __ballot_sync(FULL_MASK, ford(cm[j][c]) >= thr[j]);
-                while (hit) {
-                    const int w = __ffs(hit) - 1;
-                    hit &= hit - 1;
-                    if (tm_half) {
-                        rescan_tmem<RES_TM_STATES / 128>(q[j], tbase, j, w, c, nu_t, tmp[j], thr[j], sdelta, a.LAd, a.K, icol[j], lane);
-                    } else {
-                        for (int u = lane; u < nu_s; u += 32) {
-                            const int k = S + 4 * (w + 32 * u) + c;
-                            if (k < a.K) {
-                                const float pre = __fadd_rn(tmp[j], sdelta[k]);
-                                if (ford(__fadd_rn(pre, *rest_ptr(rr[j], k))) >= thr[j])
-                                    pending_push(q[j], pre, k, a.LAd + (size_t)k * a.K + icol[j]);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        if (tracing) tr[3] = clock64();
-        // ---- exact (value, first index) of each half, then of the pair ------------------------------
-#pragma unroll
-        for (int j = 0; j < RCOLS; ++j) {
-            const Best r = pending_finish(q[j]);  // (-FLT_MAX, -1) when this half holds no candidate
-            if (lane == 0) ps.bx[half][j] = r.x, ps.bk[half][j] = r.k;
-        }
-        named_bar_sync(2 + pair, 64);
-        // the tensor-memory warp publishes columns 0 and 1, the shared-memory warp 2 and 3: lanes 0/1 one each
-#pragma unroll
-        for (int j = 0; j < RCOLS; ++j) {
-            if ((j >> 1) != half || (j & 1) != lane || !have[j]) continue;
-            Best r{ps.bx[0][j], ps.bk[0][j]};
-            if (r.k < 0) r.k = 0x7fffffff;
-            const int k1 = ps.bk[1][j];
-            best_take(r, ps.bx[1][j], k1 < 0 ? 0x7fffffff : k1);
-            if (!(r.x > -FLT_MAX)) r.x = -FLT_MAX, r.k = -1;
-            const int i = icol[j];
-            publish_delta(xout, i, r.x, (int)step_tag(a, s));
-            if (last_step) a.d_final[i] = r.x;
-            if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (jstep - a.mid - 1)) * a.K + i, r.k);
-        }
-        if (tracing) tr[4] = clock64();
-        named_bar_sync(1, NCONS);  // sdelta is overwritten by the next step's load; the pair slots by the next step
-        if (tracing) tr[5] = clock64();
-    }
-    tmem_fence_before();
-    named_bar_sync(1, NCONS);
-    if (warp == 0) tmem_dealloc(*tmem_slot);
-}
-
 // ---- host side ---------------------------------------------------------------------------------
 static size_t persist_smem(int Kp, int nstage)
 {
@@ -964,16 +709,19 @@ static int launch_persist(flashv_model *m, PersistArgs &a)
     const int grid = ctx->sm_count < a.ncol ? ctx->sm_count : a.ncol;  // the grid the tiled table was laid out for
     const int cols_max = (a.ncol + grid - 1) / grid;
     const bool use_tmem = cols_max <= TILE_RW && Kp >= TILE_CH && env_int("FLASHV_TMEM", 1) != 0;
-    // the whole slice on chip (k_flash_resident): single GPU, one round of columns, and the part of the slice
-    // that tensor memory cannot take must fit shared memory beside the delta vector
-    int res_S = Kp / TILE_CH * TILE_CH;
-    if (res_S > RES_TM_STATES) res_S = RES_TM_STATES;
-    const size_t res_smem = CTRL_BYTES + (size_t)Kp * 4 + RP * sizeof(PairSlot) + (size_t)(Kp - res_S) * cols_max * 4;
-    const bool use_res = a.npeer == 1 && cols_max <= RES_MAX_COLS && res_smem <= (size_t)ctx->smem_optin &&
-                         env_int("FLASHV_RESIDENT", 1) != 0;
-    if (use_res) smem = res_smem;
-    const void *fn = use_res ? (const void *)k_flash_resident
-                             : (use_tmem ? (const void *)k_flash_persist<true> : (const void *)k_flash_persist<false>);
+    // Pinned ring: with the first 2048 states of every column in tensor memory, what is left of a CTA's slice
+    // (207 KB at K=3965 on 148 SMs) may fit shared memory whole.  Then it is loaded once: no refill traffic
+    // (TMA writes cost the shared-memory pipe as much as the reads), no per-stage barrier hand-shakes, no L2 reads.
+    a.pinned = 0;
+    if (use_tmem && env_int("FLASHV_PIN", 1) != 0) {
+        const int nk_res = std::min(TM_RES_CHUNKS, Kp / TILE_CH), nk = (Kp + TILE_CH - 1) / TILE_CH;
+        const size_t rest = (size_t)(Kp - nk_res * TILE_CH) * cols_max * sizeof(float);
+        if (nk - nk_res <= MAX_STAGES && fixed + rest <= (size_t)ctx->smem_optin) {
+            a.pinned = 1, a.nstage = std::max(1, nk - nk_res);
+            smem = fixed + std::max(rest, (size_t)16);
+        }
+    }
+    const void *fn = use_tmem ? (const void *)k_flash_persist<true> : (const void *)k_flash_persist<false>;
     FV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     FV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NTHREADS, smem));
@@ -991,7 +739,7 @@ static int launch_persist(flashv_model *m, PersistArgs &a)
         FV_CUDA(cudaMemsetAsync(d_trace, 0, trace_n * sizeof(long long), ctx->stream));
         a.trace = d_trace;
     }
-    void *params[] = {(void *)&a, (void *)&res_S};  // the ring kernels take the first argument only
+    void *params[] = {(void *)&a};
     // cooperative launch: every CTA polls data the others produce, so all must be co-resident;
     // the grid is the one the tiled table was laid out for
     FV_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NTHREADS), params, smem, ctx->stream));

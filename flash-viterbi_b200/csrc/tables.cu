@@ -77,6 +77,12 @@ void build_tiled_slice(const double *LAd, float *hiC, int K, int Kp, int col_beg
     k_build_tiled<<<dim3((ncol + 255) / 256, Kp), 256, 0, st>>>(LAd, hiC, K, Kp, col_begin, ncol, G);
 }
 
+static bool prep_trace() { return getenv("FLASHV_PREP_TRACE") != nullptr; }
+static double ms_since(std::chrono::steady_clock::time_point t0)
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
 static int host_threads(int share)
 {
     int nthr = 0;
@@ -147,6 +153,7 @@ int tables_logs(flashv_model *m, const float *A, const float *B, const float *Pi
         ctx->h_prep_bytes = stage_bytes;
     }
     const int nthr = host_threads(share);
+    if (prep_trace()) fprintf(stderr, "[flashv prep] checks + pinned staging: %.2f ms, %d host threads\n", ms_since(t0), nthr);
     std::atomic<int> bad{0};
     cudaEvent_t drained[2] = {ctx->ev_prep[0], ctx->ev_prep[1]};
     int nchunk = 0;
@@ -164,7 +171,10 @@ int tables_logs(flashv_model *m, const float *A, const float *B, const float *Pi
             for (long long c = c0; c < c1; ++c) {
                 const float v = src[c];
                 good &= (v >= 0.0f && v <= 1.0f);
-                stage[c] = log((double)v);  // F:170
+                // F:170.  log(+0) is -inf by definition (C Annex F), but glibc reaches it through its error
+                // path (errno, FE_DIVBYZERO) at several times the cost of a regular call — and 1-p of a
+                // data_script.py table is exactly 0.
+                stage[c] = v == 0.0f ? -INFINITY : log((double)v);
             }
             if (!good) bad.store(1);
         };
@@ -186,6 +196,7 @@ int tables_logs(flashv_model *m, const float *A, const float *B, const float *Pi
         return FLASHV_ERR_DOMAIN;
     }
 
+    if (prep_trace()) fprintf(stderr, "[flashv prep] log A rows [%d,%d) issued: %.2f ms\n", row_lo, row_hi, ms_since(t0));
     std::vector<double> hLB((size_t)M * K), hLPi((size_t)K);
     std::vector<float> hLBf((size_t)M * Kp, 0.0f);
     for (int i = 0; i < K; ++i) {
@@ -201,6 +212,7 @@ int tables_logs(flashv_model *m, const float *A, const float *B, const float *Pi
     FV_CUDA(cudaMemcpyAsync(m->LPi, hLPi.data(), hLPi.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     FV_CUDA(cudaStreamSynchronize(ctx->stream));  // the vectors are on this frame; the staging buffers are reusable
     m->row_lo = row_lo, m->row_hi = row_hi;
+    if (prep_trace()) fprintf(stderr, "[flashv prep] logs uploaded: %.2f ms\n", ms_since(t0));
     m->prep_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return FLASHV_OK;
 }
@@ -228,9 +240,14 @@ int tables_layouts(flashv_model *m)
     m->tile_G = ctx->sm_count < K ? ctx->sm_count : K;
     build_tiled_slice(m->LAd, m->hiC, K, Kp, 0, K, m->tile_G, ctx->stream);
     FV_CUDA(cudaGetLastError());
+    if (prep_trace()) {
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "[flashv prep] dense layouts: %.2f ms\n", ms_since(t0));
+    }
     const int rc = sparse_build(m);
     if (rc != FLASHV_OK) return rc;
     FV_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (prep_trace()) fprintf(stderr, "[flashv prep] + edge lists: %.2f ms\n", ms_since(t0));
     m->ready = true;
     m->prep_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return FLASHV_OK;

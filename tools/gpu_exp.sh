@@ -1,12 +1,14 @@
 #!/bin/bash
-# scratch script for the experiment at hand: the whole GPU suite, smoke() and a short bench against HEAD
+# scratch script for the experiment at hand: persistent kernel variants — parity, timing, phase trace
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/gpus.txt 2>&1; nproc >> gpurun_out/gpus.txt; free -g >> gpurun_out/gpus.txt
-timeout 1500 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -15 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err
-echo "bench exit $?"
-tail -c 600 gpurun_out/bench.err
-python tools/summarize_bench.py gpurun_out/bench.log 2>/dev/null | head -60
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 -p no:cacheprovider -k "trellis_step or goldens or golden_vectors or bench_instance_flash or random_models or wide_model or headline_flash_vs" > gpurun_out/pytest_res.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_res.log
+tail -4 gpurun_out/pytest_res.log
+for P in 0 1; do
+FLASHV_PIN=$P timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-extras > gpurun_out/bench_pin$P.log 2> gpurun_out/bench_pin$P.err
+echo "bench PIN=$P exit $?"; tail -c 300 gpurun_out/bench_pin$P.err
+done
+python tools/summarize_bench.py gpurun_out/bench_pin0.log gpurun_out/bench_pin1.log
+FLASHV_TRACE_FILE=gpurun_out/trace.bin python tools/profile_target.py --engine persistent --segments 127 --iters 3 > gpurun_out/trace_run.log 2>&1
+python tools/trace_report.py gpurun_out/trace.bin > gpurun_out/trace_report.txt 2>&1
+cat gpurun_out/trace_run.log gpurun_out/trace_report.txt
