@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "flashv_ctx_create", "flashv_ctx_destroy", "flashv_ctx_stream", "flashv_ctx_sync", "flashv_ctx_sm_count",
     "flashv_model_create", "flashv_model_destroy", "flashv_model_K", "flashv_model_M", "flashv_model_prep_ms",
     "flashv_read_floats_text", "flashv_read_ints_text",
-    "flashv_decode", "flashv_bs_decode", "flashv_decode_batch", "flashv_bs_decode_batch",
+    "flashv_decode", "flashv_bs_decode", "flashv_decode_batch", "flashv_bs_decode_batch", "flashv_vanilla_decode",
     "flashv_plan_create", "flashv_plan_destroy", "flashv_plan_upload", "flashv_plan_run",
     "flashv_plan_download", "flashv_plan_report",
     "flashv_plan_shard_init", "flashv_plan_shard_buffers", "flashv_plan_shard_ipc_handle",
@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "flashv_model_finish", "flashv_shard_count", "flashv_decode_batch_shard",
     "flashv_mgpu_create", "flashv_mgpu_destroy", "flashv_mgpu_world", "flashv_mgpu_ctx", "flashv_mgpu_model",
     "flashv_mgpu_model_create", "flashv_mgpu_decode_batch", "flashv_mgpu_decode",
-    "flashv_read_floats_cached", "flashv_trellis_init", "flashv_trellis_step", "flashv_bs_score_step", "flashv_bs_heap_replay",
+    "flashv_read_floats_cached", "flashv_trellis_init", "flashv_trellis_step", "flashv_trellis_step_columns_dev", "flashv_bs_score_step", "flashv_bs_heap_replay",
     "flashv_task_list", "flashv_executed_steps", "flashv_memory_bytes", "flashv_bs_memory_bytes",
 ]
 
@@ -111,6 +111,7 @@ def lib():
     L.flashv_read_ints_text.restype = C.c_long
     L.flashv_decode.argtypes = [vp, ip, C.c_int, C.c_int, ip, fp, rp]
     L.flashv_bs_decode.argtypes = [vp, ip, C.c_int, C.c_int, C.c_int, ip, fp, rp]
+    L.flashv_vanilla_decode.argtypes = [vp, ip, C.c_int, ip, fp, rp]
     L.flashv_decode_batch.argtypes = [vp, ip, C.c_int, C.c_int, C.c_int, ip, fp, rp]
     L.flashv_bs_decode_batch.argtypes = [vp, ip, C.c_int, C.c_int, C.c_int, C.c_int, ip, fp, rp]
     L.flashv_plan_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
@@ -145,6 +146,7 @@ def lib():
     L.flashv_mgpu_decode.argtypes = [vp, ip, C.c_int, C.c_int, ip, fp, rp]
     L.flashv_trellis_init.argtypes = [vp, C.c_int, C.c_int, fp]
     L.flashv_trellis_step.argtypes = [vp, fp, C.c_int, fp, ip, C.c_int]
+    L.flashv_trellis_step_columns_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
     L.flashv_bs_score_step.argtypes = [vp, fp, ip, C.c_int, C.c_int, fp, ip]
     L.flashv_bs_heap_replay.argtypes = [vp, fp, C.c_int, C.c_int, fp, ip]
     L.flashv_task_list.argtypes = [C.c_int, C.c_int, ip, ip, ip, ip]
@@ -330,6 +332,14 @@ class Model:
         _check(lib().flashv_decode(self._h, _i(ob), ob.shape[0], N, _i(path), C.byref(score), C.byref(rep)))
         return path, np.float32(score.value), rep
 
+    def vanilla_decode(self, ob):
+        """The reference's vanilla Viterbi baseline (sanity path, its own arithmetic): (path[T], score, report)."""
+        ob = np.ascontiguousarray(ob, np.int32)
+        path = np.empty(ob.shape[0], np.int32)
+        score, rep = C.c_float(), Report()
+        _check(lib().flashv_vanilla_decode(self._h, _i(ob), ob.shape[0], _i(path), C.byref(score), C.byref(rep)))
+        return path, np.float32(score.value), rep
+
     def bs_decode(self, ob, N, B):
         """calc() of FLASH-BS (S:548-577)."""
         ob = np.ascontiguousarray(ob, np.int32)
@@ -361,6 +371,11 @@ class Model:
         psi = np.empty(self.K, np.int32)
         _check(lib().flashv_trellis_step(self._h, _f(delta_in), int(o), _f(d), _i(psi), engine))
         return d, psi
+
+    def trellis_step_columns_dev(self, delta_in_ptr, o, col_begin, col_end, delta_out_ptr, psi_out_ptr):
+        """One step over the destination states [col_begin, col_end), device pointers, asynchronous."""
+        _check(lib().flashv_trellis_step_columns_dev(self._h, C.c_void_p(delta_in_ptr), int(o), int(col_begin), int(col_end),
+                                                     C.c_void_p(delta_out_ptr), C.c_void_p(psi_out_ptr)))
 
     def bs_score_step(self, hval, hstate, o):
         hval = np.ascontiguousarray(hval, np.float32)

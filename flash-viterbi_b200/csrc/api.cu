@@ -783,6 +783,18 @@ extern "C" int flashv_trellis_step(flashv_model *m, const float *delta_in, int o
     return FLASHV_OK;
 }
 
+extern "C" int flashv_trellis_step_columns_dev(flashv_model *m, const void *delta_in_dev, int o, int col_begin, int col_end,
+                                               void *delta_out_dev, void *psi_out_dev)
+{
+    if (!m || !delta_in_dev || !delta_out_dev || !psi_out_dev || o < 0 || o >= m->M || col_begin < 0 || col_end > m->K ||
+        col_begin >= col_end || m->Kp > STEP_MAX_KP) {
+        set_error("flashv_trellis_step_columns_dev: bad argument");
+        return FLASHV_ERR_ARG;
+    }
+    FV_CUDA(cudaSetDevice(m->ctx->device));
+    return flash_step_columns(m, (const float *)delta_in_dev, o, col_begin, col_end, (float *)delta_out_dev, (int32_t *)psi_out_dev);
+}
+
 extern "C" int flashv_bs_score_step(flashv_model *m, const float *heap_val, const int32_t *heap_state, int B, int o,
                                     float *score_out, int32_t *arg_slot_out)
 {

@@ -104,6 +104,7 @@ struct StepArgs {
     int T;
     void *psi;
     int psi16;
+    int c_begin = 0, c_end = 0;  // destination columns this launch computes: [c_begin, c_end), 0/0 = all K
 };
 
 template <int QB, int RI, int NWARP>
@@ -135,17 +136,18 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
         }
     }
 
-    const int ntiles = (a.K + NWARP * RI - 1) / (NWARP * RI);
+    const int c_begin = a.c_end > 0 ? a.c_begin : 0, c_end = a.c_end > 0 ? a.c_end : a.K;
+    const int ntiles = (c_end - c_begin + NWARP * RI - 1) / (NWARP * RI);
     for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
-        const int ibase = (tile * NWARP + warp) * RI;
-        if (ibase >= a.K) continue;  // warp-uniform; no block-wide barrier below
+        const int ibase = c_begin + (tile * NWARP + warp) * RI;
+        if (ibase >= c_end) continue;  // warp-uniform; no block-wide barrier below
         int col_i[RI];
         const float4 *col4[RI];
         float tmp[RI][QB];
         float cm[RI][QB][4];
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
-            col_i[r] = min(ibase + r, a.K - 1);  // a clamped duplicate column is computed and dropped
+            col_i[r] = min(ibase + r, c_end - 1);  // a clamped duplicate column is computed and dropped
             col4[r] = reinterpret_cast<const float4 *>(a.hiT + (size_t)col_i[r] * a.Kp);
 #pragma unroll
             for (int q = 0; q < QB; ++q) {
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
         // trips of all QB pairs overlap
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
-            if (ibase + r >= a.K) continue;  // warp-uniform: the clamped duplicate column
+            if (ibase + r >= c_end) continue;  // warp-uniform: the clamped duplicate column
             const int i = ibase + r;
             const float *pcol[QB];
             const float *pdelta[QB];
@@ -371,7 +373,8 @@ static cudaError_t launch_step(const StepArgs &a, int nact, int sm_count, cudaSt
     cudaError_t e = cudaFuncSetAttribute(k_flash_step<QB, RI, NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
     const int ngroups = (nact + QB - 1) / QB;
-    const int ntiles = (a.K + NWARP * RI - 1) / (NWARP * RI);
+    const int ncols = a.c_end > 0 ? a.c_end - a.c_begin : a.K;
+    const int ntiles = (ncols + NWARP * RI - 1) / (NWARP * RI);
     // blocks that fit at once (shared memory bound), spread over the vector groups
     int per_sm = smem ? (int)((200 * 1024) / smem) : 8;
     per_sm = per_sm < 1 ? 1 : (per_sm > 2048 / (NWARP * 32) ? 2048 / (NWARP * 32) : per_sm);
@@ -499,6 +502,25 @@ int flash_single_step(flashv_model *m, const float *d_in_dev, int o, float *d_ou
     a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.vecs = dv, a.nact = 1, a.s = 1, a.din = d_in_dev, a.dout = d_out_dev;
     a.ob = dob, a.T = 2, a.psi = psi_dev, a.psi16 = 0;
+    FV_CUDA((launch_step<1, 1, 8>(a, 1, ctx->sm_count, ctx->stream)));
+    return FLASHV_OK;
+}
+
+// One step of ONE vector over the destination columns [c_begin, c_end) only, everything device-resident
+// (tools/nccl_baseline.py: the state-sharded pass with the delta exchange done by ncclAllGather between
+// per-step launches — the baseline the in-kernel peer stores are measured against).
+int flash_step_columns(flashv_model *m, const float *d_in_dev, int o, int c_begin, int c_end, float *d_out_dev, int32_t *psi_dev)
+{
+    flashv_ctx *ctx = m->ctx;
+    VecDesc *dv = reinterpret_cast<VecDesc *>(m->scratch_i);
+    int32_t *dob = m->scratch_i + 16;
+    k_one_vec<<<1, 1, 0, ctx->stream>>>(dv, dob, o);
+    FV_CUDA(cudaGetLastError());
+    StepArgs a;
+    a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+    a.vecs = dv, a.nact = 1, a.s = 1, a.din = d_in_dev, a.dout = d_out_dev;
+    a.ob = dob, a.T = 2, a.psi = psi_dev, a.psi16 = 0;
+    a.c_begin = c_begin, a.c_end = c_end;
     FV_CUDA((launch_step<1, 1, 8>(a, 1, ctx->sm_count, ctx->stream)));
     return FLASHV_OK;
 }

@@ -185,6 +185,7 @@ inline void *pass_psi(const flashv_plan *p, const Pass &pass)
 
 int flash_single_step(flashv_model *m, const float *d_in_dev, int o, float *d_out_dev, int32_t *psi_dev, int engine);
 int flash_single_init(flashv_model *m, int prev_state, int o, float *d_out_dev);
+int flash_step_columns(flashv_model *m, const float *d_in_dev, int o, int c_begin, int c_end, float *d_out_dev, int32_t *psi_dev);
 int bs_single_score(flashv_model *m, const float *hv_dev, const int32_t *hs_dev, int B, int o, float *score_dev,
                     int32_t *arg_dev);
 int bs_single_replay(flashv_ctx *ctx, const float *score_dev, int K, int B, float *hv_dev, int32_t *hs_dev);

@@ -104,6 +104,15 @@ int flashv_decode_batch(flashv_model *model, const int32_t *ob, int batch, int T
 int flashv_bs_decode_batch(flashv_model *model, const int32_t *ob, int batch, int T, int N, int B,
                            int32_t *path_out, float *score_out, flashv_report *report);
 
+/* Sanity path: viterbi() of "Base_line/C implementations/vanilla Viterbi.c":124-171, the textbook
+ * decoder the reference ships as its baseline — every backpointer kept, one backtrack, and ITS arithmetic
+ * (T1 + log A + log B in double, one rounding, :140), which is not FLASH's (F:170): bit-equal to the reference's
+ * vanilla program, equal to FLASH where the reference's own two programs agree.  report->memory_bytes is that
+ * program's `memory:` line (sizeof(T1)+sizeof(T2), :172).  FLASHV_ERR_DOMAIN if the path runs through a state
+ * no transition reaches (the reference reads T2[-1] there). */
+int flashv_vanilla_decode(flashv_model *model, const int32_t *ob, int T, int32_t *path_out, float *score_out,
+                          flashv_report *report);
+
 /* ---- staged decodes (what the one-call forms do; lets a caller keep inputs resident) ---- */
 /* B == 0 selects FLASH, B >= 1 FLASH-BS. */
 int flashv_plan_create(flashv_model *model, int T, int N, int batch, int B, int engine, flashv_plan **out);
@@ -184,6 +193,13 @@ int flashv_trellis_init(flashv_model *model, int prev_state, int ob0, float *del
 /* One max-plus step (F:165-174): delta_in[K], symbol o -> delta_out[K], psi_out[K] (-1 = dead). */
 int flashv_trellis_step(flashv_model *model, const float *delta_in, int o, float *delta_out, int32_t *psi_out,
                         int engine);
+/* The same step for the destination states [col_begin, col_end) only, DEVICE pointers, asynchronous on the
+ * context's stream: delta_in_dev[Kp] (padding beyond K finite), delta_out_dev[Kp] and psi_out_dev[K] (int32)
+ * receive the entries of that range.  What a state-sharded pass looks like when the per-step exchange is
+ * left to a library collective (tools/nccl_baseline.py: ncclAllGather between launches, the baseline of
+ * SURVEY 8e) instead of the in-kernel peer stores of flashv_plan_shard_*. */
+int flashv_trellis_step_columns_dev(flashv_model *model, const void *delta_in_dev, int o, int col_begin, int col_end,
+                                    void *delta_out_dev, void *psi_out_dev);
 /* One FLASH-BS score step (S:437-446) and the heap rebuild (S:167-211). */
 int flashv_bs_score_step(flashv_model *model, const float *heap_val, const int32_t *heap_state, int B, int o,
                          float *score_out, int32_t *arg_slot_out);

@@ -22,8 +22,16 @@ import subprocess
 from pathlib import Path
 
 REF_SRC = Path("/root/reference/src")
+REF_BASELINES = Path("/root/reference/Base_line/C implementations")
 OUT_DIR = Path(__file__).resolve().parent / "_ref"
 PROGS = {"FLASH": "FLASH_Viterbi_multithread", "FLASH_BS": "FLASH_BS_Viterbi_multithread"}
+# the vanilla baseline: same knob shapes (no MAX_THREADS), built with the same recipe; its K x T tables are static
+# arrays, fine at the small sizes the sanity fixtures use
+BASELINE_PROGS = {"VANILLA": "vanilla Viterbi"}
+
+
+def _source_path(prog) -> Path:
+    return REF_BASELINES / f"{BASELINE_PROGS[prog]}.c" if prog in BASELINE_PROGS else REF_SRC / f"{PROGS[prog]}.c"
 
 
 def reference_available() -> bool:
@@ -38,7 +46,7 @@ def binary_name(prog, K, M, T, prob, N, B=None) -> str:
 
 
 def _substituted_source(prog, K, M, T, prob, N, B, data_path) -> str:
-    text = (REF_SRC / f"{PROGS[prog]}.c").read_text()
+    text = _source_path(prog).read_text()
     # run.py:29-37
     text = re.sub(r"#define K_STATE \d+", f"#define K_STATE {K}", text)
     text = re.sub(r"#define T_STATE \d+", f"#define T_STATE {M}", text)
@@ -61,8 +69,8 @@ def build(prog, K, M, T, prob, N, B=None, data_path="./data/", out_dir: Path = O
     out = out_dir / binary_name(prog, K, M, T, prob, N, B)
     if out.exists() and not force:
         return out
-    if not reference_available():
-        raise FileNotFoundError(f"{REF_SRC} not present and {out.name} was not prebuilt")
+    if not _source_path(prog).exists():
+        raise FileNotFoundError(f"{_source_path(prog)} not present and {out.name} was not prebuilt")
     src = _substituted_source(prog, K, M, T, prob, N, B, data_path)
     cmd = ["gcc", "-g", "-pthread", "-x", "c", "-", "-o", str(out), "-lm", "-Wl,-z,stack-size=268435456"]  # run.py:54
     subprocess.run(cmd, input=src.encode(), check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)

@@ -396,6 +396,63 @@ int fvo_flash_decode(const fvo_model *m, const int *ob, int T, int N, int *path,
     return 0;
 }
 
+/* ---------------------------------------------------------------- vanilla Viterbi (sanity path) */
+
+/* viterbi() of "Base_line/C implementations/vanilla Viterbi.c":124-171 (V: below).  NOT the FLASH arithmetic:
+ * the candidate is  T1[k][j-1] + log(A[k][i]) + log(B[i][o_j])  (V:140) — the float promoted to double, two
+ * double adds left to right, one rounding to float on the store; strict '>' from (-FLT_MAX, -1) (V:136-145);
+ * last column: first maximum from (-FLT_MAX, -1) (V:152-161); backtrack through the full T2 table (V:167-170).
+ * memory = sizeof(T1)+sizeof(T2) (V:172).  Returns -1 where the reference walks off its tables (a dead column
+ * on the path: arg = -1, V:147/163 only print an error).  Needs the full (non-lean) model. */
+int fvo_vanilla_decode(const fvo_model *m, const int *ob, int T, int *path, float *score, int *memory_bytes)
+{
+    const int K = m->K, M = m->M;
+    if (T < 1 || m->lean) return -1;
+    float *d0 = (float *)malloc(sizeof(float) * (size_t)K), *d1 = (float *)malloc(sizeof(float) * (size_t)K);
+    int *T2 = (int *)malloc(sizeof(int) * (size_t)K * (size_t)T);
+    for (int i = 0; i < K; ++i) d0[i] = (float)(m->LPi[i] + m->LB[(size_t)i * M + ob[0]]); /* V:120, V:128 */
+    for (int j = 1; j < T; ++j) {
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < K; ++i) {
+            const double *col = m->LAt + (size_t)i * K;
+            const double lb = m->LB[(size_t)i * M + ob[j]];
+            float best = -FLT_MAX;
+            int arg = -1;
+            for (int k = 0; k < K; ++k) {
+                float cand = (float)(((double)d0[k] + col[k]) + lb); /* V:140 */
+                if (cand > best) {
+                    best = cand;
+                    arg = k;
+                }
+            }
+            d1[i] = best;
+            T2[(size_t)i * T + j] = arg;
+        }
+        float *t = d0;
+        d0 = d1, d1 = t;
+    }
+    float best = -FLT_MAX;
+    int arg = -1;
+    for (int i = 0; i < K; ++i)
+        if (d0[i] > best) best = d0[i], arg = i; /* V:154-160 */
+    int rc = arg < 0 ? -1 : 0;
+    if (rc == 0) {
+        path[T - 1] = arg;
+        for (int j = T - 1; j > 0; --j) { /* V:167-170 */
+            const int prev = T2[(size_t)path[j] * T + j];
+            if (prev < 0) {
+                rc = -1;
+                break;
+            }
+            path[j - 1] = prev;
+        }
+    }
+    if (score) *score = best;
+    if (memory_bytes) *memory_bytes = (int)(sizeof(float) * (size_t)K * T + sizeof(int) * (size_t)K * T); /* V:172 */
+    free(d0), free(d1), free(T2);
+    return rc;
+}
+
 /* ---------------------------------------------------------------- FLASH-BS pieces */
 
 typedef struct {

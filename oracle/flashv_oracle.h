@@ -47,6 +47,12 @@ int fvo_flash_decode(const fvo_model *m, const int *ob, int T, int N,
 int fvo_bs_decode(const fvo_model *m, const int *ob, int T, int N, int Bw,
                   int *path, float *score, int *memory_bytes);
 
+/* viterbi() of "Base_line/C implementations/vanilla Viterbi.c":124-171 — the textbook O(K*T)-memory decoder the
+ * reference ships as a baseline, with ITS arithmetic (candidate = T1 + log A + log B in double, one rounding),
+ * which is not FLASH's (F:170), so paths may legitimately differ on near-ties: a sanity path, never the parity
+ * oracle of FLASH.  Returns -1 if the decoded path would run through a dead column (the reference reads T2[-1]). */
+int fvo_vanilla_decode(const fvo_model *m, const int *ob, int T, int *path, float *score, int *memory_bytes);
+
 /* One dense trellis step (F:165-174): d_out[i], psi[i] from d_in[k] and symbol o. */
 void fvo_flash_step(const fvo_model *m, const float *d_in, int o, float *d_out, int *psi);
 

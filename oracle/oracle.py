@@ -41,6 +41,7 @@ def lib():
         L.fvo_model_free.argtypes = [vp]
         L.fvo_flash_decode.argtypes = [vp, ip, C.c_int, C.c_int, ip, fp, ip]
         L.fvo_bs_decode.argtypes = [vp, ip, C.c_int, C.c_int, C.c_int, ip, fp, ip]
+        L.fvo_vanilla_decode.argtypes = [vp, ip, C.c_int, ip, fp, ip]
         L.fvo_flash_step.argtypes = [vp, fp, C.c_int, fp, ip]
         L.fvo_flash_init.argtypes = [vp, C.c_int, C.c_int, fp]
         L.fvo_bs_score_step.argtypes = [vp, fp, ip, C.c_int, C.c_int, fp, ip]
@@ -96,6 +97,17 @@ class OracleModel:
         rc = lib().fvo_flash_decode(self._h, _i(ob), T, N, _i(path), C.byref(score), C.byref(mem))
         if rc != 0:
             raise ValueError(f"oracle: unsupported (T={T}, N={N})")
+        return path, np.float32(score.value), mem.value
+
+    def vanilla(self, ob):
+        """The reference's vanilla Viterbi baseline (its own arithmetic): (path, score, memory)."""
+        ob = np.ascontiguousarray(ob, dtype=np.int32)
+        T = ob.shape[0]
+        path = np.empty(T, np.int32)
+        score, mem = C.c_float(), C.c_int()
+        rc = lib().fvo_vanilla_decode(self._h, _i(ob), T, _i(path), C.byref(score), C.byref(mem))
+        if rc != 0:
+            raise ValueError("oracle: the vanilla decoder's path runs through a dead column (outside the reference's domain)")
         return path, np.float32(score.value), mem.value
 
     def flash_bs(self, ob, N, Bw):

@@ -515,3 +515,32 @@ def test_bench_instance_flash_bs(fv, oracle_mod, bench_instance, N, Bw, ob_seed,
     assert np.array_equal(got, want), (N, Bw, np.nonzero(got != want)[0][:8])
     assert _bits(score) == _bits(wscore) and rep.memory_bytes == wmem
     assert ((want < 0).sum() > 0) == dropouts
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_vanilla_sanity_path(fv, oracle_mod, golden_models, name):
+    """flashv_vanilla_decode against what the reference's own vanilla program printed for the same
+    model and sequence, the oracle's restatement (score bits), and FLASH's path (equal on these instances)."""
+    from conftest import ROOT
+
+    v = np.load(ROOT / "tests" / "golden" / "vanilla.npz")
+    g = load_golden(name)
+    model = golden_models[name]
+    om = oracle_mod.OracleModel(g["A"], g["B"], g["Pi"])
+    for si, ob in enumerate(g["obs"]):
+        path, score, rep = model.vanilla_decode(ob)
+        assert np.array_equal(path, v[f"{name}__{si}__path"])
+        assert rep.memory_bytes == int(v[f"{name}__{si}__memory"]) and rep.kernel_launches == len(ob) + 1
+        assert _bits(score) == _bits(om.vanilla(ob)[1])
+        assert np.array_equal(path, model.decode(ob, 3)[0])
+
+
+def test_vanilla_on_bench_instance(fv, oracle_mod, bench_instance):
+    """The sanity relation at the headline size: vanilla and FLASH (N=127) decode the same path on the bench's
+    own model and sequence; vanilla's score equals the oracle restatement's bit for bit."""
+    model, A, B, Pi, ob = bench_instance
+    om = oracle_mod.OracleModel(A, B, Pi)
+    path, score, rep = model.vanilla_decode(ob)
+    want, wscore, _ = om.vanilla(ob)
+    assert np.array_equal(path, want) and _bits(score) == _bits(wscore)
+    assert np.array_equal(path, model.decode(ob, 127)[0])

@@ -109,3 +109,20 @@ def test_lean_oracle_equals_literal(oracle_mod, name):
         path, score, mem = lean.flash(case["ob"], case["N"])
         assert np.array_equal(path, case["path"]) and mem == case["memory"]
         assert np.float32(score).view(np.uint32) == np.float32(full.flash(case["ob"], case["N"])[1]).view(np.uint32)
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_vanilla_oracle_matches_reference_baseline(oracle_mod, name):
+    """the restatement of the reference's vanilla Viterbi baseline against the outputs of the
+    baseline program itself (tests/golden/make_golden_vanilla.py), and the sanity relation README:71 claims —
+    here FLASH and vanilla decode the same path on every frozen instance (not guaranteed in general: the two
+    programs add in a different order, "vanilla Viterbi.c":140 vs F:170)."""
+    from conftest import ROOT
+
+    v = np.load(ROOT / "tests" / "golden" / "vanilla.npz")
+    g = load_golden(name)
+    om = oracle_mod.OracleModel(g["A"], g["B"], g["Pi"])
+    for si, ob in enumerate(g["obs"]):
+        path, score, mem = om.vanilla(ob)
+        assert np.array_equal(path, v[f"{name}__{si}__path"]) and mem == int(v[f"{name}__{si}__memory"])
+        assert np.array_equal(path, om.flash(ob, 1)[0])
