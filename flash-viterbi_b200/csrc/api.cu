@@ -291,6 +291,22 @@ static void add_pass(flashv_plan *p, std::vector<VecDesc> &all, const std::vecto
     p->passes.push_back(std::move(ps));
 }
 
+// Device copy of every pass's nactive[] (the persistent level kernel walks it step by step).
+static int upload_nactive(flashv_plan *p)
+{
+    std::vector<int> all;
+    for (Pass &ps : p->passes) {
+        ps.nactive_off = all.size();
+        all.insert(all.end(), ps.nactive.begin(), ps.nactive.end());
+        all.push_back(0);
+    }
+    cudaFree(p->d_nactive);
+    p->d_nactive = nullptr;
+    FV_CUDA(cudaMalloc(&p->d_nactive, (all.size() + 1) * sizeof(int)));
+    FV_CUDA(cudaMemcpy(p->d_nactive, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return FLASHV_OK;
+}
+
 extern "C" int flashv_plan_create(flashv_model *m, int T, int N, int batch, int B, int engine, flashv_plan **out)
 {
     if (!m || !out || batch < 1 || B < 0) {
@@ -396,6 +412,7 @@ extern "C" int flashv_plan_create(flashv_model *m, int T, int N, int batch, int 
         (e = cudaMemcpyAsync(p->d_ismid, ismid.data(), (size_t)T, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
         fail(e, "upload ismid");
     if (rc == FLASHV_OK && (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) fail(e, "sync");
+    if (rc == FLASHV_OK) rc = upload_nactive(p);
     if (rc != FLASHV_OK) {
         flashv_plan_destroy(p);
         return rc;
@@ -414,6 +431,7 @@ extern "C" void flashv_plan_destroy(flashv_plan *p)
     cudaFree(p->hiC_shard), cudaFree(p->shard_region), cudaFree(p->d_lvl_mid);
     cudaFree(p->d_ob), cudaFree(p->d_ans), cudaFree(p->d_score), cudaFree(p->d_delta), cudaFree(p->d_psi);
     cudaFree(p->d_vecs), cudaFree(p->d_ismid), cudaFree(p->d_endstate), cudaFree(p->d_sync), cudaFree(p->d_bs_score);
+    cudaFree(p->d_nactive);
     delete p;
 }
 
@@ -451,7 +469,7 @@ static int shard_spread_levels(flashv_plan *p)
     FV_CUDA(cudaMalloc(&p->d_lvl_mid, (mids.size() + 1) * sizeof(int32_t)));
     FV_CUDA(cudaMemcpyAsync(p->d_lvl_mid, mids.data(), mids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, p->model->ctx->stream));
     FV_CUDA(cudaStreamSynchronize(p->model->ctx->stream));
-    return FLASHV_OK;
+    return upload_nactive(p);
 }
 
 extern "C" int flashv_plan_shard_init(flashv_plan *p, int rank, int world)

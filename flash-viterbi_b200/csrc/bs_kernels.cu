@@ -175,6 +175,7 @@ struct BsArgs {
     int flagbit;        // backpointer-entry bit "several beam states attain this maximum"
     float *rows;        // [psi rows][K] score vectors of the steps mid .. R-1 (row of step j-1 = backpointer row of step j)
     int always_replay;  // FLASHV_BS_REPLAY=1: rebuild the heap by replay at every step (the slow, literal path)
+    int score_buf1_off;  // floats from the first score vector to the second one (end of the CTA's other buffers)
     const uint8_t *ismid;
     long long *trace;  // optional: per CTA {score cycles, beam cycles} (FLASHV_BS_TRACE), else null
 };
@@ -305,7 +306,11 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
     const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     float *smem_f = reinterpret_cast<float *>(smem_f4);
     const int K = a.K, B = a.B, T = a.T;
-    float *sscore = smem_f;
+    // Two score vectors: step j writes vector j&1 of every CTA while the slower CTAs may still be building
+    // their beam from vector (j-1)&1 — one cluster barrier per step instead of two ("all scores arrived"; the
+    // "everybody is done reading" barrier is implied: vector j&1 was last read two steps ago, before the
+    // reader arrived at the barrier of step j-1).
+    float *sscore0 = smem_f, *sscore1 = smem_f + a.score_buf1_off;
     HeapNode *beam = reinterpret_cast<HeapNode *>(smem_f + a.Kp);
     HeapNode *node = beam + ((B + 1) & ~1);
     BeamScratch *bs = reinterpret_cast<BeamScratch *>(node + 2 * B + 4);
@@ -320,10 +325,10 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
     // states per CTA: 8/CS consecutive eighths of the state range (the eighths are where the out-edge lists are cut)
     const int per8 = (K + 7) / 8, q_lo = rank * (8 / CS), q_hi = q_lo + 8 / CS;
     const int s_lo = min(K, q_lo * per8), s_hi = min(K, q_hi * per8);
-    float *peer_score[8];
+    float *peer_score0[8];  // every CTA's vector 0 (vector 1 sits score_buf1_off floats further in each of them)
 #pragma unroll
-    for (int r = 0; r < 8; ++r) peer_score[r] = r < CS ? cluster.map_shared_rank(sscore, r) : sscore;
-    auto keep_row = [&](int j) {  // the scores of step j are the "previous scores" of backpointer row j+1
+    for (int r = 0; r < 8; ++r) peer_score0[r] = r < CS ? cluster.map_shared_rank(sscore0, r) : sscore0;
+    auto keep_row = [&](int j, const float *sscore) {  // the scores of step j are the "previous scores" of backpointer row j+1
         if (j < vd.mid || j > vd.R - 1) return;
         float *dst = a.rows + (size_t)(vd.psi_row + (j - vd.mid)) * K;
         for (int i = s_lo + tid; i < s_hi; i += nthr) dst[i] = sscore[i];
@@ -334,15 +339,16 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
     {
         const int prev = vd.L == 0 ? -1 : ans[vd.L - 1];
         const int o = ob[vd.L];
+        float *sstart = (vd.L & 1) ? sscore1 : sscore0;
         for (int i = tid; i < K; i += nthr) {
             const double head = prev < 0 ? a.LPi[i] : a.LAd[(size_t)prev * K + i];
-            sscore[i] = __double2float_rn(__dadd_rn(head, a.LBd[(size_t)o * K + i]));
+            sstart[i] = __double2float_rn(__dadd_rn(head, a.LBd[(size_t)o * K + i]));
         }
     }
     __syncthreads();
-    keep_row(vd.L);
-    bool have_heap = build_beam(sscore, K, B, beam, node, bs, a.always_replay || (full && vd.R == vd.L));
-    cluster.sync();  // every CTA is done reading its start vector before anyone's step-1 scores arrive
+    keep_row(vd.L, (vd.L & 1) ? sscore1 : sscore0);
+    bool have_heap = build_beam((vd.L & 1) ? sscore1 : sscore0, K, B, beam, node, bs, a.always_replay || (full && vd.R == vd.L));
+    cluster.sync();  // every CTA of the cluster is running (its shared memory may be written) before anyone's step-1 scores arrive
 
     long long t_score = 0, t_beam = 0;
     const int Bh = (B + 1) >> 1;
@@ -350,6 +356,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
         const long long c0 = clock64();
         const int o = ob[j];
         const bool keep = j >= vd.mid + 1;  // S:448: payload latches at j == mid+1
+        const int boff = (j & 1) ? a.score_buf1_off : 0;  // this step's score vector
+        float *sscore = (j & 1) ? sscore1 : sscore0;
         if (a.csr_cut) {
             // ---- scoring over the out-edges of the beam states (S:437-446 restricted to the candidates that
             // can win: an entry with A[s][i] == 0 gives -inf and never passes the strict '>').  Warp per
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
                 const bool tie = scnt[t] > 1;
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
-                    if (r < CS) peer_score[r][i] = best;
+                    if (r < CS) peer_score0[r][boff + i] = best;
                 // with the true heap in beam[] (slot order) the smallest slot IS the reference's choice
                 if (keep) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + i,
                                     arg >= 0 && tie && !have_heap ? arg | a.flagbit : arg);
@@ -481,18 +489,18 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
                     tie = true;
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
-                    if (r < CS) peer_score[r][i] = best;
+                    if (r < CS) peer_score0[r][boff + i] = best;
                 // with the true heap in beam[] (slot order) the first maximum IS the reference's choice
                 if (keep) psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + i,
                                     arg >= 0 && tie && !have_heap ? arg | a.flagbit : arg);
             }
         }
         }
-        cluster.sync();  // all scores of step j are in every CTA's vector
+        cluster.sync();  // all scores of step j are in every CTA's vector j&1
         const long long c1 = clock64();
-        keep_row(j);
+        keep_row(j, sscore);
         have_heap = build_beam(sscore, K, B, beam, node, bs, a.always_replay || (full && j == vd.R));
-        cluster.sync();  // every CTA is done reading the scores of step j
+        __syncthreads();  // the beam is complete before this CTA's warps score step j+1 from it
         t_score += c1 - c0, t_beam += clock64() - c1;
     }
     if (rank != 0) return;
@@ -538,11 +546,13 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
     }
 }
 
-static size_t bs_smem_bytes(int Kp, int B)
+static size_t bs_smem_base(int Kp, int B)
 {
     // + the sparse scoring's per-destination key / slot / count arrays (at most all K states in one CTA)
-    return (size_t)Kp * 4 + (size_t)(((B + 1) & ~1) + 2 * B + 4) * sizeof(HeapNode) + sizeof(BeamScratch) + (size_t)3 * Kp * 4 + 16;
+    size_t n = (size_t)Kp * 4 + (size_t)(((B + 1) & ~1) + 2 * B + 4) * sizeof(HeapNode) + sizeof(BeamScratch) + (size_t)3 * Kp * 4 + 16;
+    return (n + 15) & ~(size_t)15;
 }
+static size_t bs_smem_bytes(int Kp, int B) { return bs_smem_base(Kp, B) + (size_t)Kp * 4; }  // + the second score vector
 
 int bs_run_pass(flashv_plan *p, const Pass &pass)
 {
@@ -558,6 +568,7 @@ int bs_run_pass(flashv_plan *p, const Pass &pass)
     a.psi = p->d_psi, a.psi16 = p->psi16, a.ismid = p->d_ismid;
     a.flagbit = p->psi16 ? 0x8000 : 0x40000000, a.rows = p->d_bs_score;
     a.always_replay = getenv("FLASHV_BS_REPLAY") ? atoi(getenv("FLASHV_BS_REPLAY")) : 0;  // read per call: tests toggle it
+    a.score_buf1_off = (int)(bs_smem_base(m->Kp, p->B) / sizeof(float));
     a.trace = nullptr;
     static long long *d_trace = nullptr;
     const bool tracing = getenv("FLASHV_BS_TRACE") != nullptr;

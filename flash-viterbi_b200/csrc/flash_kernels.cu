@@ -18,20 +18,27 @@
 namespace flashv {
 
 // ---- start vectors: F:142 / F:212 (pi form) and F:150 / F:220 (restart from Ans[L-1]) ------
+__device__ __forceinline__ void init_vector(const VecDesc &vd, int v, const int32_t *__restrict__ ob,
+                                            const int32_t *__restrict__ ans, int T, const double *__restrict__ LAd,
+                                            const double *__restrict__ LBd, const double *__restrict__ LPi, int K, int Kp,
+                                            float *__restrict__ delta, int i_first, int i_stride)
+{
+    const int prev = vd.L == 0 ? -1 : ans[(size_t)vd.seq * T + vd.L - 1];
+    const int o = ob[(size_t)vd.seq * T + vd.L];
+    for (int i = i_first; i < K; i += i_stride) {
+        const double head = prev < 0 ? LPi[i] : LAd[(size_t)prev * K + i];
+        delta[(size_t)v * Kp + i] = __double2float_rn(__dadd_rn(head, LBd[(size_t)o * K + i]));
+    }
+}
+
 __global__ void k_flash_init(const VecDesc *__restrict__ vecs, int nvec, const int32_t *__restrict__ ob,
                              const int32_t *__restrict__ ans, int T, const double *__restrict__ LAd,
                              const double *__restrict__ LBd, const double *__restrict__ LPi, int K, int Kp,
                              float *__restrict__ delta)
 {
-    for (int v = blockIdx.y; v < nvec; v += gridDim.y) {
-        const VecDesc vd = vecs[v];
-        const int prev = vd.L == 0 ? -1 : ans[(size_t)vd.seq * T + vd.L - 1];
-        const int o = ob[(size_t)vd.seq * T + vd.L];
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
-            const double head = prev < 0 ? LPi[i] : LAd[(size_t)prev * K + i];
-            delta[(size_t)v * Kp + i] = __double2float_rn(__dadd_rn(head, LBd[(size_t)o * K + i]));
-        }
-    }
+    for (int v = blockIdx.y; v < nvec; v += gridDim.y)
+        init_vector(vecs[v], v, ob, ans, T, LAd, LBd, LPi, K, Kp, delta, blockIdx.x * blockDim.x + threadIdx.x,
+                    gridDim.x * blockDim.x);
 }
 
 // Running maxima of the float estimate for an RI x QB tile (RI destination columns, QB delta
@@ -107,19 +114,22 @@ struct StepArgs {
     int c_begin = 0, c_end = 0;  // destination columns this launch computes: [c_begin, c_end), 0/0 = all K
 };
 
+// The body of one step for vector group `group` by column worker `worker` of `nworkers` (standalone: one
+// launch per step, grid = groups x workers; persistent level kernel: the same CTA comes back every step).
+// delta is read with ld.global.cg: in the persistent kernel it was written by other SMs one grid barrier ago.
 template <int QB, int RI, int NWARP>
-__global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
+__device__ __forceinline__ void step_body(const StepArgs &a, int step, int nact, const float *__restrict__ din, float *__restrict__ dout,
+                                          int group, int worker, int nworkers, float4 *sdelta4)
 {
-    extern __shared__ float4 sdelta4[];
     constexpr int NT = NWARP * 32;
     const int Kp4 = a.Kp >> 2;
-    const int v0 = blockIdx.x * QB;  // vector groups on x (no 65535 cap), column workers on y
+    const int v0 = group * QB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int q = 0; q < QB; ++q) {
-        const bool live = v0 + q < a.nact;
-        const float4 *src = reinterpret_cast<const float4 *>(a.din + (size_t)(v0 + q) * a.Kp);
-        for (int t = tid; t < Kp4; t += NT) sdelta4[q * Kp4 + t] = live ? src[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool live = v0 + q < nact;
+        const float4 *src = reinterpret_cast<const float4 *>(din + (size_t)(v0 + q) * a.Kp);
+        for (int t = tid; t < Kp4; t += NT) sdelta4[q * Kp4 + t] = live ? __ldcg(src + t) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     const float *sdelta = reinterpret_cast<const float *>(sdelta4);
@@ -129,16 +139,16 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
 #pragma unroll
     for (int q = 0; q < QB; ++q) {
         jj[q] = 0, tmp_row[q] = a.LBf;
-        if (v0 + q < a.nact) {
+        if (v0 + q < nact) {
             const VecDesc vd = a.vecs[v0 + q];
-            jj[q] = vd.L + a.s;
+            jj[q] = vd.L + step;
             tmp_row[q] = a.LBf + (size_t)a.ob[(size_t)vd.seq * a.T + jj[q]] * a.Kp;  // F:167
         }
     }
 
     const int c_begin = a.c_end > 0 ? a.c_begin : 0, c_end = a.c_end > 0 ? a.c_end : a.K;
     const int ntiles = (c_end - c_begin + NWARP * RI - 1) / (NWARP * RI);
-    for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
+    for (int tile = worker; tile < ntiles; tile += nworkers) {
         const int ibase = c_begin + (tile * NWARP + warp) * RI;
         if (ibase >= c_end) continue;  // warp-uniform; no block-wide barrier below
         int col_i[RI];
@@ -176,9 +186,9 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
             resolve_tile<QB>(cm[r], tmp[r], pcol, pdelta, picol, a.LAd, a.K, a.Kp, lane, res);
 #pragma unroll
             for (int q = 0; q < QB; ++q) {
-                if (v0 + q >= a.nact) continue;  // warp-uniform: padding vector of the last group
+                if (v0 + q >= nact) continue;  // warp-uniform: padding vector of the last group
                 if (lane == 0) {
-                    a.dout[(size_t)(v0 + q) * a.Kp + i] = res[q].x;
+                    dout[(size_t)(v0 + q) * a.Kp + i] = res[q].x;
                     const VecDesc vd = a.vecs[v0 + q];
                     if (jj[q] >= vd.mid + 1)  // F:242: only steps from the latch on are ever read back
                         psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (jj[q] - vd.mid - 1)) * a.K + i, res[q].k);
@@ -186,6 +196,13 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
             }
         }
     }
+}
+
+template <int QB, int RI, int NWARP>
+__global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
+{
+    extern __shared__ float4 sdelta4[];
+    step_body<QB, RI, NWARP>(a, a.s, a.nact, a.din, a.dout, blockIdx.x, blockIdx.y, gridDim.y, sdelta4);  // vector groups on x (no 65535 cap), column workers on y
 }
 
 // ---- the last step of a task needs one column ---------------------------------------------------
@@ -198,35 +215,36 @@ __global__ void __launch_bounds__(NWARP * 32) k_flash_step(const StepArgs a)
 // elements u = w, w + LC_WARPS, ... of every chain (lane, component) of trellis_common.cuh; same
 // estimate / window / exact logic as every other kernel, combined across warps in shared memory.
 constexpr int LC_WARPS = 8;
-__global__ void __launch_bounds__(LC_WARPS * 32) k_flash_last_column(const StepArgs a, int v_begin, const int32_t *__restrict__ ans)
+// Executed by a whole CTA of at least LC_WARPS warps (the first LC_WARPS work, all take the barriers).
+__device__ __forceinline__ void last_column_body(const StepArgs &a, int step, const float *__restrict__ din, int v,
+                                                 const int32_t *__restrict__ ans)
 {
     __shared__ float s_top[LC_WARPS];
     __shared__ float s_bx[LC_WARPS];
     __shared__ int s_bk[LC_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int v = v_begin + blockIdx.x;  // a.nact: one past the last vector on its final step
     const VecDesc vd = a.vecs[v];
-    const int j = vd.L + a.s;  // == vd.R
+    const int j = vd.L + step;  // == vd.R
     const int e = ans[(size_t)vd.seq * a.T + vd.R];
     if (e < 0 || e >= a.K) return;  // CTA-uniform
     const float tmp = __ldg(a.LBf + (size_t)a.ob[(size_t)vd.seq * a.T + j] * a.Kp + e);  // F:233
     const float *col = a.hiT + (size_t)e * a.Kp;
-    const float *delta = a.din + (size_t)v * a.Kp;
+    const float *delta = din + (size_t)v * a.Kp;
     const float4 *col4 = reinterpret_cast<const float4 *>(col);
     const float4 *d4 = reinterpret_cast<const float4 *>(delta);
     const int Kp4 = a.Kp >> 2;
     float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 4
-    for (int t = 32 * warp + lane; t < Kp4; t += 32 * LC_WARPS) {
+    for (int t = 32 * warp + lane; t < Kp4 && warp < LC_WARPS; t += 32 * LC_WARPS) {
         const float4 h = __ldg(col4 + t);
-        const float4 d = __ldg(d4 + t);
+        const float4 d = __ldcg(d4 + t);
         cm[0] = fmaxf(cm[0], __fadd_rn(__fadd_rn(tmp, d.x), h.x));
         cm[1] = fmaxf(cm[1], __fadd_rn(__fadd_rn(tmp, d.y), h.y));
         cm[2] = fmaxf(cm[2], __fadd_rn(__fadd_rn(tmp, d.z), h.z));
         cm[3] = fmaxf(cm[3], __fadd_rn(__fadd_rn(tmp, d.w), h.w));
     }
     const float wtop = warp_max(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
-    if (lane == 0) s_top[warp] = wtop;
+    if (lane == 0 && warp < LC_WARPS) s_top[warp] = wtop;
     __syncthreads();
     float top = s_top[0];
 #pragma unroll
@@ -237,11 +255,11 @@ __global__ void __launch_bounds__(LC_WARPS * 32) k_flash_last_column(const StepA
         // every lane re-reads its own elements of the chains whose maximum is inside the window
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            if (ford(cm[c]) < thr) continue;
+            if (ford(cm[c]) < thr || warp >= LC_WARPS) continue;
             for (int t = 32 * warp + lane; t < Kp4; t += 32 * LC_WARPS) {
                 const int k = 4 * t + c;
                 if (k >= a.K) break;
-                const float pre = __fadd_rn(tmp, __ldg(delta + k));
+                const float pre = __fadd_rn(tmp, __ldcg(delta + k));
                 if (ford(__fadd_rn(pre, __ldg(col + k))) >= thr) {
                     const float x = exact_cand(pre, __ldg(a.LAd + (size_t)k * a.K + e));
                     if (x > -FLT_MAX) best_take(b, x, k);
@@ -250,7 +268,7 @@ __global__ void __launch_bounds__(LC_WARPS * 32) k_flash_last_column(const StepA
         }
     }
     b = warp_best(b);
-    if (lane == 0) s_bx[warp] = b.x, s_bk[warp] = b.k;
+    if (lane == 0 && warp < LC_WARPS) s_bx[warp] = b.x, s_bk[warp] = b.k;
     __syncthreads();
     if (threadIdx.x == 0) {
         Best r{s_bx[0], s_bk[0]};
@@ -259,25 +277,27 @@ __global__ void __launch_bounds__(LC_WARPS * 32) k_flash_last_column(const StepA
         if (!(r.x > -FLT_MAX)) r.k = -1;
         psi_store(a.psi, a.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * a.K + e, r.k);
     }
+    __syncthreads();  // the shared slots are reused by the CTA's next vector
+}
+
+__global__ void __launch_bounds__(LC_WARPS * 32) k_flash_last_column(const StepArgs a, int v_begin, const int32_t *__restrict__ ans)
+{
+    last_column_body(a, a.s, a.din, v_begin + blockIdx.x, ans);
 }
 
 // ---- end of a full-range pass: Ans[T-1] = first argmax of delta (F:188-195, F:251-258) ----
-__global__ void __launch_bounds__(256) k_flash_end(const VecDesc *__restrict__ vecs, int nvec,
-                                                   const float *__restrict__ delta, int K, int Kp, int T,
-                                                   int32_t *__restrict__ ans, float *__restrict__ score,
-                                                   int32_t *__restrict__ endstate)
+// Executed by a whole CTA (any size up to 32 warps).
+__device__ __forceinline__ void end_body(const VecDesc &vd, int v, const float *__restrict__ delta, int K, int Kp, int T,
+                                         int32_t *__restrict__ ans, float *__restrict__ score, int32_t *__restrict__ endstate)
 {
-    const int v = blockIdx.x;
-    if (v >= nvec) return;
-    const VecDesc vd = vecs[v];
-    __shared__ float sx[8];
-    __shared__ int sk[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ float sx[32];
+    __shared__ int sk[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = (blockDim.x + 31) >> 5;
     if (vd.flags & VEC_FULL_RANGE) {
         // "score = T1[cur][0]; arg = 0; if (T1[cur][i] > score)": first maximum, index 0 if all equal.
         Best b{-INFINITY, 0x7fffffff};
-        for (int i = tid; i < K; i += 256) {
-            float x = delta[(size_t)v * Kp + i];
+        for (int i = tid; i < K; i += blockDim.x) {
+            float x = __ldcg(delta + (size_t)v * Kp + i);
             if (x > b.x || (x == b.x && i < b.k)) b.x = x, b.k = i;
         }
         b = warp_best(b);
@@ -285,34 +305,59 @@ __global__ void __launch_bounds__(256) k_flash_end(const VecDesc *__restrict__ v
         __syncthreads();
         if (tid == 0) {
             Best r{sx[0], sk[0]};
-            for (int w = 1; w < 8; ++w) best_take(r, sx[w], sk[w]);
+            for (int w = 1; w < nwarp; ++w) best_take(r, sx[w], sk[w]);
             if (r.k == 0x7fffffff) r.k = 0;  // every entry -inf: the reference keeps arg = 0
             ans[(size_t)vd.seq * T + vd.R] = r.k;
-            score[vd.seq] = delta[(size_t)v * Kp + r.k];
+            score[vd.seq] = __ldcg(delta + (size_t)v * Kp + r.k);
             endstate[v] = r.k;
         }
+        __syncthreads();
     } else if (tid == 0) {
         endstate[v] = ans[(size_t)vd.seq * T + vd.R];  // F:248
     }
 }
 
+__global__ void __launch_bounds__(256) k_flash_end(const VecDesc *__restrict__ vecs, int nvec,
+                                                   const float *__restrict__ delta, int K, int Kp, int T,
+                                                   int32_t *__restrict__ ans, float *__restrict__ score,
+                                                   int32_t *__restrict__ endstate)
+{
+    const int v = blockIdx.x;
+    if (v >= nvec) return;
+    end_body(vecs[v], v, delta, K, Kp, T, ans, score, endstate);
+}
+
 // ---- non-recursive backtrack through the stored rows --------------------------------------
 // One thread per vector: state_{j-1} = psi_j[state_j] for j = R .. mid+1.  A task records
 // Ans[mid] (F:261); the first pass records every segment boundary it walks over (F:198-201).
+// (rows are read with ld.global.cg: in the persistent level kernel other SMs wrote them a grid barrier ago)
+__device__ __forceinline__ int psi_load_cg(const void *base, int psi16, size_t idx)
+{
+    if (psi16) {
+        const unsigned v = __ldcg(reinterpret_cast<const uint16_t *>(base) + idx);
+        return v == 0xFFFFu ? -1 : (int)v;
+    }
+    return __ldcg(reinterpret_cast<const int32_t *>(base) + idx);
+}
+
+__device__ __forceinline__ void backtrack_vector(const VecDesc &vd, int state, const void *__restrict__ psi, int psi16, int K, int T,
+                                                 const uint8_t *__restrict__ ismid, int32_t *__restrict__ ans)
+{
+    int32_t *out = ans + (size_t)vd.seq * T;
+    for (int j = vd.R; j >= vd.mid + 1; --j) {
+        if (state >= 0) state = psi_load_cg(psi, psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + state);
+        if ((vd.flags & VEC_FIRST_PASS) && ismid[j - 1]) out[j - 1] = state;
+    }
+    if (!(vd.flags & VEC_FIRST_PASS)) out[vd.mid] = state;
+}
+
 __global__ void k_flash_backtrack(const VecDesc *__restrict__ vecs, int nvec, const void *__restrict__ psi, int psi16,
                                   int K, int T, const uint8_t *__restrict__ ismid,
                                   const int32_t *__restrict__ endstate, int32_t *__restrict__ ans)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nvec) return;
-    const VecDesc vd = vecs[v];
-    int state = endstate[v];
-    int32_t *out = ans + (size_t)vd.seq * T;
-    for (int j = vd.R; j >= vd.mid + 1; --j) {
-        if (state >= 0) state = psi_load(psi, psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + state);
-        if ((vd.flags & VEC_FIRST_PASS) && ismid[j - 1]) out[j - 1] = state;
-    }
-    if (!(vd.flags & VEC_FIRST_PASS)) out[vd.mid] = state;
+    backtrack_vector(vecs[v], endstate[v], psi, psi16, K, T, ismid, ans);
 }
 
 // The same walk for ONE long vector (the first pass: T-1-mids[0] dependent hops).  A hop through
@@ -364,6 +409,134 @@ __global__ void __launch_bounds__(1024) k_flash_backtrack_staged(const VecDesc *
     if (threadIdx.x == 0 && !(vd.flags & VEC_FIRST_PASS)) out[vd.mid] = s_state;
 }
 
+// ---- one level of the task tree in ONE launch ---------------------------------------------------------
+// The reference's worker pool (F:264-308) runs the tasks of the tree on MAX_THREADS host threads; here one
+// cooperative kernel per level keeps every SM on the level's tasks from their start vectors to their
+// midpoints: start vectors (F:212/F:220), every trellis step of every task in lock-step (grid barrier
+// between steps; the step itself is step_body, the tasks on their last step take last_column_body), the
+// end states (F:248-259) and the walk back to Ans[mid] (F:261).  One launch instead of 3 + 2 per step.
+// Grid barrier of the level kernel: one monotone 64-bit counter per plan.  Every CTA adds 1 and waits until
+// the counter reaches (barriers so far) x (CTAs); the host tells each launch where the count stands
+// (bar_base), so nothing is reset and a CTA that starts late cannot misread an earlier generation.  All
+// CTAs are co-resident (cooperative launch).  The grid-wide sync of cooperative_groups did the same job in
+// the first version and cost more per step than a kernel launch.
+__device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1ull);
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(bar) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+}
+
+struct LevelArgs {
+    StepArgs st;           // tables, vectors, observations, backpointer store (s, nact, din, dout are set per step)
+    const double *LBd, *LPi;
+    int nvec, max_steps, full_range;
+    const int *nactive;    // [max_steps + 2]: vectors still stepping at step s (a prefix of the order)
+    float *d0, *d1;        // delta ping-pong, [nvec][Kp] each
+    int32_t *ans;
+    float *score;
+    int32_t *endstate;
+    const uint8_t *ismid;
+    unsigned long long *bar;      // the plan's barrier counter
+    unsigned long long bar_base;  // its value when this launch starts
+};
+
+template <int QB, int RI, int NWARP>
+__global__ void __launch_bounds__(NWARP * 32) k_flash_level(const LevelArgs la)
+{
+    extern __shared__ float4 sdelta4[];
+    unsigned long long bar_target = la.bar_base;
+    const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
+    const int K = la.st.K, Kp = la.st.Kp, T = la.st.T;
+    for (int v = b; v < la.nvec; v += G)
+        init_vector(la.st.vecs[v], v, la.st.ob, la.ans, T, la.st.LAd, la.LBd, la.LPi, K, Kp, la.d0, tid, NWARP * 32);
+    grid_barrier(la.bar, bar_target += gridDim.x);
+    for (int s = 1; s <= la.max_steps; ++s) {
+        // vectors are sorted longest first: [0, n_cont) go on after this step, [n_cont, n_act) are on
+        // their last step and (unless the pass is full-range) need a single column
+        const int n_act = la.nactive[s], n_cont = la.full_range ? n_act : la.nactive[s + 1];
+        const float *din = (s & 1) ? la.d0 : la.d1;
+        float *dout = (s & 1) ? la.d1 : la.d0;
+        if (n_cont > 0) {
+            const int ngroups = (n_cont + QB - 1) / QB;
+            const int workers = G / ngroups > 0 ? G / ngroups : 1;
+            for (int item = b; item < ngroups * workers; item += G) {  // one item per CTA unless there are more groups than CTAs
+                step_body<QB, RI, NWARP>(la.st, s, n_cont, din, dout, item / workers, item % workers, workers, sdelta4);
+                __syncthreads();  // the staged deltas are replaced by the next item's
+            }
+        }
+        for (int v = n_cont + b; v < n_act; v += G) last_column_body(la.st, s, din, v, la.ans);
+        grid_barrier(la.bar, bar_target += gridDim.x);
+    }
+    const float *final_delta = (la.max_steps & 1) ? la.d1 : la.d0;
+    for (int v = b; v < la.nvec; v += G) {
+        const VecDesc vd = la.st.vecs[v];
+        end_body(vd, v, final_delta, K, Kp, T, la.ans, la.score, la.endstate);
+        if (tid == 0) backtrack_vector(vd, la.endstate[v], la.st.psi, la.st.psi16, K, T, la.ismid, la.ans);
+        __syncthreads();
+    }
+}
+
+template <int QB, int RI, int NWARP>
+static int launch_level(flashv_plan *p, const Pass &pass, LevelArgs &la, bool *done)
+{
+    flashv_ctx *ctx = p->model->ctx;
+    const size_t smem = (size_t)QB * la.st.Kp * sizeof(float);
+    const void *fn = (const void *)k_flash_level<QB, RI, NWARP>;
+    FV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    int per_sm = 0;
+    FV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NWARP * 32, smem));
+    if (per_sm < 1) return FLASHV_OK;  // does not fit: the caller falls back to one launch per step
+    if (per_sm > 4) per_sm = 4;
+    const int ngroups = (pass.nvec + QB - 1) / QB;
+    const int ntiles = (la.st.K + NWARP * RI - 1) / (NWARP * RI);
+    int grid = per_sm * ctx->sm_count;
+    if (grid > ngroups * ntiles) grid = ngroups * ntiles;  // no more CTAs than (group, tile) items
+    if (grid < 1) grid = 1;
+    la.bar = reinterpret_cast<unsigned long long *>(p->d_sync), la.bar_base = p->bar_count;
+    p->bar_count += (unsigned long long)(1 + pass.max_steps) * grid;  // one barrier after the start vectors, one per step
+    void *params[] = {(void *)&la};
+    FV_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NWARP * 32), params, smem, ctx->stream));
+    ++p->launches;
+    *done = true;
+    return FLASHV_OK;
+}
+
+// Returns with *done = true when the whole pass (start vectors .. Ans[mid]) ran in one launch.
+static int level_pass(flashv_plan *p, const Pass &pass, bool *done)
+{
+    flashv_model *m = p->model;
+    *done = false;
+    if (!m->ctx->coop || !p->d_nactive || getenv("FLASHV_LEVEL_STEPS")) return FLASHV_OK;
+    // Measured (K=3965, T=256, same box): one launch per level against one per step — N=1 9.65 / 10.12 ms, N=8
+    // 6.29 / 6.53 ms, N=64 2.77 / 2.75 ms, N=127 2.22 / 2.16 ms.  A level of one or two steps has nothing to
+    // amortise the extra grid barriers over, so short levels keep the per-step launches.
+    const int min_steps = getenv("FLASHV_LEVEL_MIN_STEPS") ? atoi(getenv("FLASHV_LEVEL_MIN_STEPS")) : 5;
+    if (pass.max_steps < min_steps) return FLASHV_OK;
+    LevelArgs la;
+    StepArgs &a = la.st;
+    a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+    a.vecs = p->d_vecs + pass.vec_offset, a.nact = 0, a.s = 0, a.din = nullptr, a.dout = nullptr;
+    a.ob = p->d_ob, a.T = p->T, a.psi = p->d_psi, a.psi16 = p->psi16;
+    la.LBd = m->LBd, la.LPi = m->LPi;
+    la.nvec = pass.nvec, la.max_steps = pass.max_steps, la.full_range = pass.full_range ? 1 : 0;
+    la.nactive = p->d_nactive + pass.nactive_off;
+    la.d0 = p->d_delta, la.d1 = p->d_delta + (size_t)p->max_vec * m->Kp;
+    la.ans = p->d_ans, la.score = p->d_score, la.endstate = p->d_endstate, la.ismid = p->d_ismid;
+    const size_t vec_bytes = (size_t)m->Kp * 4;
+    if (pass.nvec >= 5 && 8 * vec_bytes <= 200 * 1024) return launch_level<8, 2, 16>(p, pass, la, done);
+    if (pass.nvec >= 3 && 4 * vec_bytes <= 200 * 1024) return launch_level<4, 2, 8>(p, pass, la, done);
+    if (2 * vec_bytes <= 200 * 1024) return launch_level<2, 1, 8>(p, pass, la, done);
+    return FLASHV_OK;
+}
+
 // ---- host orchestration -------------------------------------------------------------------------
 template <int QB, int RI, int NWARP>
 static cudaError_t launch_step(const StepArgs &a, int nact, int sm_count, cudaStream_t st)
@@ -413,6 +586,16 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
     const bool sparse = p->engine == FLASHV_ENGINE_SPARSE && pass.nvec == 1;
     // many vectors over a table small enough that the deltas of a group stay in shared memory (flash_group.cu)
     const bool grouped = p->engine != FLASHV_ENGINE_STEP && pass.nvec >= 2 * ctx->sm_count && group_engine_fits(m);
+    if (!grouped && p->engine == FLASHV_ENGINE_PERSISTENT && pass.nvec >= 2 && !pass_is_sharded(p, pass)) {
+        // a level of the task tree (or a small batch's N-way pass): everything in one cooperative launch
+        bool done = false;
+        int rc = level_pass(p, pass, &done);
+        if (rc != FLASHV_OK) return rc;
+        if (done) {
+            if (time_it) FV_CUDA(cudaEventRecord(ctx->ev[3], st));
+            return FLASHV_OK;
+        }
+    }
     if (!grouped) {  // the group kernel builds its start vectors itself
         dim3 ig((K + 255) / 256, pass.nvec < 65535 ? pass.nvec : 65535);
         k_flash_init<<<ig, 256, 0, st>>>(vecs, pass.nvec, p->d_ob, p->d_ans, T, m->LAd, m->LBd, m->LPi, K, Kp, d0);

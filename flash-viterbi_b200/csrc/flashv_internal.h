@@ -62,6 +62,7 @@ struct Pass {
     int psi_rows = 0;    // rows of the backpointer store this pass needs
     size_t vec_offset = 0;  // into the plan's device VecDesc array
     std::vector<int> nactive;  // nactive[s] = vectors still stepping at step s (1-based), prefix of the order
+    size_t nactive_off = 0;    // where this pass's nactive[] starts in the plan's device copy
     bool full_range = false;
     VecDesc first_vec{};  // host copy of vector 0 (single-vector passes are driven from it)
 };
@@ -131,8 +132,10 @@ struct flashv_plan {
     void *d_psi = nullptr;        // [max psi_rows][K] u16 or i32
     flashv::VecDesc *d_vecs = nullptr;
     uint8_t *d_ismid = nullptr;   // [T] 1 where a first-pass segment boundary sits
+    int *d_nactive = nullptr;     // every pass's nactive[] back to back (the persistent level kernel reads it)
     int32_t *d_endstate = nullptr;  // [max_vec]
-    unsigned int *d_sync = nullptr; // grid-barrier words of the persistent engine
+    unsigned int *d_sync = nullptr; // 256 zeroed bytes: the level kernel's grid-barrier counter (64-bit, monotone)
+    unsigned long long bar_count = 0;  // what that counter holds once every launch issued so far has finished
     // state sharding of single-vector passes
     int shard_rank = 0, shard_world = 1;
     int shard_c0 = 0, shard_ncol = 0;   // destination columns this GPU owns
