@@ -125,12 +125,24 @@ __device__ __forceinline__ void step_body(const StepArgs &a, int step, int nact,
     const int Kp4 = a.Kp >> 2;
     const int v0 = group * QB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // staging with cp.async (global -> shared without a register in between, L2 only): all QB vectors are
+    // requested at once and the CTA pays ONE memory round trip — the load/store loop this replaces paid one per
+    // vector (ncu: 22 % of an 8-vector step, all of it long-scoreboard stalls on the stores)
 #pragma unroll
     for (int q = 0; q < QB; ++q) {
         const bool live = v0 + q < nact;
         const float4 *src = reinterpret_cast<const float4 *>(din + (size_t)(v0 + q) * a.Kp);
-        for (int t = tid; t < Kp4; t += NT) sdelta4[q * Kp4 + t] = live ? __ldcg(src + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = tid; t < Kp4; t += NT) {
+            if (live)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdelta4 + q * Kp4 + t)),
+                             "l"(src + t)
+                             : "memory");
+            else
+                sdelta4[q * Kp4 + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     const float *sdelta = reinterpret_cast<const float *>(sdelta4);
 

@@ -544,3 +544,47 @@ def test_vanilla_on_bench_instance(fv, oracle_mod, bench_instance):
     want, wscore, _ = om.vanilla(ob)
     assert np.array_equal(path, want) and _bits(score) == _bits(wscore)
     assert np.array_equal(path, model.decode(ob, 127)[0])
+
+
+@pytest.mark.parametrize("mode", ["every_level", "never"])
+def test_level_kernel_and_step_launches_agree(fv, oracle_mod, golden_models, monkeypatch, mode):
+    """The tree levels run either as one cooperative launch per level (k_flash_level: start vectors, all steps,
+    one-column last steps, end states and the walk back inside one kernel) or as one launch per step; the
+    library picks by level length.  Forced both ways here — every level through the level kernel, and none —
+    on the golden cases (including levels of a single step) and on the headline-shaped random model."""
+    if mode == "every_level":
+        monkeypatch.setenv("FLASHV_LEVEL_MIN_STEPS", "1")
+    else:
+        monkeypatch.setenv("FLASHV_LEVEL_STEPS", "1")
+    for name in GOLDEN_NAMES:
+        model = golden_models[name]
+        for case in golden_cases(name):
+            if case["prog"] != 0:
+                continue
+            plan = fv.Plan(model, len(case["ob"]), case["N"], 1, 0, fv.ENGINE_PERSISTENT)
+            plan.upload(case["ob"])
+            plan.run()
+            paths, _ = plan.download()
+            launches = plan.report().kernel_launches
+            plan.close()
+            assert np.array_equal(paths[0], case["path"]), (name, mode, case["N"])
+            assert launches > 0
+    A, B, Pi = random_hmm(1500, 11, 0.2, 77)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    rng = np.random.RandomState(77)
+    obs = rng.randint(0, 11, (3, 90)).astype(np.int32)
+    ctx = fv.Context(0)
+    model = fv.Model(ctx, A, B, Pi)
+    for N in (1, 2, 5, 11):
+        for b in range(2):
+            want, wscore, _ = om.flash(obs[b], N)
+            got, score, _ = model.decode(obs[b], N)
+            assert np.array_equal(got, want) and _bits(score) == _bits(wscore), (mode, N, b)
+        # a small batch: several sequences per level, K too large for the group engine's buffers? no — 1500 fits;
+        # force the plain engines by a batch below the group engine's threshold
+        paths, scores, _ = model.decode_batch(obs, N)
+        for b in range(3):
+            want, wscore, _ = om.flash(obs[b], N)
+            assert np.array_equal(paths[b], want) and _bits(scores[b]) == _bits(wscore), (mode, N, b)
+    model.close()
+    ctx.close()
