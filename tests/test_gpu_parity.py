@@ -588,3 +588,22 @@ def test_level_kernel_and_step_launches_agree(fv, oracle_mod, golden_models, mon
             assert np.array_equal(paths[b], want) and _bits(scores[b]) == _bits(wscore), (mode, N, b)
     model.close()
     ctx.close()
+
+
+def test_more_vector_groups_than_grid_y(fv, oracle_mod, gpu_ctx):
+    """A deep tree level of a large batch on the per-step engine: 2050 sequences x 256 tasks = 524,800 vectors,
+    65,600 groups of 8 — more than gridDim.y allows (65,535).  The groups sit on gridDim.x."""
+    K, M, T, batch = 20, 4, 1024, 2050
+    A, B, Pi = random_hmm(K, M, 0.6, 61)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    obs = np.random.RandomState(61).randint(0, M, (batch, T)).astype(np.int32)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+    plan = fv.Plan(model, T, 1, batch, 0, fv.ENGINE_STEP)
+    plan.upload(obs)
+    plan.run()
+    paths, scores = plan.download()
+    plan.close()
+    model.close()
+    for b in (0, 1, 1024, 2048, 2049):
+        want, wscore, _ = om.flash(obs[b], 1)
+        assert np.array_equal(paths[b], want) and _bits(scores[b]) == _bits(wscore), b
