@@ -117,3 +117,34 @@ def test_host_programs_read_dag_named_files(fv, tmp_path):
             assert pick(ours.stdout, "path:") == pick(ref.stdout, "path:")
             for kind in ("A", "B", "Pi", "ob"):  # the next program must find the _DAG names only
                 build_ref.data_file(data, kind, K, T, 0.9).unlink()
+
+
+@pytest.mark.gpu
+def test_run_py_writes_the_reference_csv(fv, tmp_path, monkeypatch):
+    """host/run.py end to end, as src/run.py would be used (R:95-107): substitute, compile, run both programs on the
+    K=64 data set, append one row per run to result/<program>_result.csv with the reference's nine columns first
+    (R:105) and the extra ones after; a second invocation appends without repeating the header."""
+    import csv
+
+    import run as host_run
+
+    g = _write_k64_text(tmp_path)
+    monkeypatch.setattr(host_run, "parameters", [dict(P64), dict(P64, MAX_THREADS=3, BeamSearchWidth=16)])
+    monkeypatch.chdir(tmp_path)
+    argv = ["run.py", "--data", "./data/", "--result", str(tmp_path / "result"), "--build-dir", str(tmp_path / "build_host")]
+    for _ in range(2):
+        monkeypatch.setattr(sys, "argv", argv)
+        host_run.main()
+    for program in host_run.PROGRAMS:
+        rows = list(csv.reader(open(tmp_path / "result" / f"{program}_result.csv", encoding="utf-8")))
+        assert rows[0] == host_run.HEADER + host_run.EXTRA and rows[0][:9] == ["timestamp", "K_STATE", "T_STATE", "obserRouteLEN",
+                                                                              "prob", "MAX_THREADS", "BeamSearchWidth", "time", "memory"]
+        assert len(rows) == 1 + 4  # two parameter sets, two invocations, one header
+        for row in rows[1:]:
+            d = dict(zip(rows[0], row))
+            assert d["K_STATE"] == "64" and d["obserRouteLEN"] == "256" and float(d["time"]) >= 0 and int(d["memory"]) > 0
+            assert float(d["time_including_prep"]) >= float(d["time"]) and int(d["executed_steps"]) > 0
+        # the memory column is the reference's formula: the golden run recorded the same number
+        row8 = [c for c in range(len(g["case_prog"])) if g["case_prog"][c] == (1 if "BS" in program else 0)
+                and g["case_seq"][c] == 0 and g["case_N"][c] == 8 and g["case_B"][c] == (8 if "BS" in program else 0)][0]
+        assert int(rows[1][8]) == int(g["case_memory"][row8])
