@@ -61,20 +61,42 @@ __device__ __forceinline__ void tile_accumulate(float (&cm)[RI][QB][4], const fl
         }                                                                                            \
     }
     if (QB * RI >= 8) {
-        float4 h1[RI], h2[RI];
+        // three statically named buffers, each re-requested three iterations ahead right after its use: no
+        // register rotation (a MOV of a register whose load is still in flight waits for the load — ncu showed
+        // the rotation's MOVs stalled on the long scoreboard as often as the FADDs issued)
+        float4 hA[RI], hB[RI], hC[RI];
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
-            h1[r] = __ldg(col4[r] + lane);
-            h2[r] = lane + 32 < Kp4 ? __ldg(col4[r] + lane + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            hA[r] = __ldg(col4[r] + lane);
+            hB[r] = lane + 32 < Kp4 ? __ldg(col4[r] + lane + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            hC[r] = lane + 64 < Kp4 ? __ldg(col4[r] + lane + 64) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (int t = lane; t < Kp4; t += 32) {
-            float4 h[RI];
+#pragma unroll 1
+        for (int t0 = lane; t0 < Kp4; t0 += 96) {
+            {
+                const int t = t0;
+                FV_ACC(hA)
+                if (t + 96 < Kp4) {
 #pragma unroll
-            for (int r = 0; r < RI; ++r) {
-                h[r] = h1[r], h1[r] = h2[r];
-                if (t + 64 < Kp4) h2[r] = __ldg(col4[r] + t + 64);
+                    for (int r = 0; r < RI; ++r) hA[r] = __ldg(col4[r] + t + 96);
+                }
             }
-            FV_ACC(h)
+            if (t0 + 32 < Kp4) {
+                const int t = t0 + 32;
+                FV_ACC(hB)
+                if (t + 96 < Kp4) {
+#pragma unroll
+                    for (int r = 0; r < RI; ++r) hB[r] = __ldg(col4[r] + t + 96);
+                }
+            }
+            if (t0 + 64 < Kp4) {
+                const int t = t0 + 64;
+                FV_ACC(hC)
+                if (t + 96 < Kp4) {
+#pragma unroll
+                    for (int r = 0; r < RI; ++r) hC[r] = __ldg(col4[r] + t + 96);
+                }
+            }
         }
     } else {
         constexpr int UNROLL = QB * RI >= 2 ? 4 : 8;
