@@ -350,7 +350,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
     bool have_heap = build_beam((vd.L & 1) ? sscore1 : sscore0, K, B, beam, node, bs, a.always_replay || (full && vd.R == vd.L));
     cluster.sync();  // every CTA of the cluster is running (its shared memory may be written) before anyone's step-1 scores arrive
 
-    long long t_score = 0, t_beam = 0;
+    long long t_score = 0, t_beam = 0, t_beam_max = 0;
+    int n_replay = 0;
     const int Bh = (B + 1) >> 1;
     for (int j = vd.L + 1; j <= vd.R; ++j) {
         const long long c0 = clock64();
@@ -501,10 +502,14 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pass(const BsArgs a)
         keep_row(j, sscore);
         have_heap = build_beam(sscore, K, B, beam, node, bs, a.always_replay || (full && j == vd.R));
         __syncthreads();  // the beam is complete before this CTA's warps score step j+1 from it
-        t_score += c1 - c0, t_beam += clock64() - c1;
+        {
+            const long long tb = clock64() - c1;
+            t_score += c1 - c0, t_beam += tb, t_beam_max = tb > t_beam_max ? tb : t_beam_max;
+            n_replay += have_heap ? 1 : 0;
+        }
     }
     if (rank != 0) return;
-    if (a.trace && tid == 0) a.trace[2 * v] = t_score, a.trace[2 * v + 1] = t_beam;
+    if (a.trace && tid == 0 && v == 0) a.trace[0] = t_score, a.trace[1] = t_beam, a.trace[2] = t_beam_max, a.trace[3] = n_replay;
 
     // ---- end state: S:374-383 / S:454-463 for a full-range pass, Find_T3_State (S:73-86) otherwise ----
     if (tid == 0) {
@@ -601,11 +606,11 @@ int bs_run_pass(flashv_plan *p, const Pass &pass)
     FV_CUDA(cudaGetLastError());
     ++p->launches;
     if (a.trace) {
-        long long h[2];
+        long long h[4];
         FV_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         FV_CUDA(cudaStreamSynchronize(ctx->stream));
-        fprintf(stderr, "[flashv bs trace] nvec=%d steps=%d vector 0: score %lld cycles, beam %lld cycles\n", pass.nvec,
-                pass.max_steps, h[0], h[1]);
+        fprintf(stderr, "[flashv bs trace] nvec=%d steps=%d vector 0: score %lld cycles, beam %lld cycles (slowest step %lld), %lld steps replayed the heap\n",
+                pass.nvec, pass.max_steps, h[0], h[1], h[2], h[3]);
     }
     return FLASHV_OK;
 }
