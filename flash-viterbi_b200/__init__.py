@@ -39,9 +39,9 @@ ABI_SYMBOLS = [
     "flashv_plan_shard_init", "flashv_plan_shard_buffers", "flashv_plan_shard_ipc_handle",
     "flashv_plan_shard_set_peer", "flashv_plan_shard_open_peer",
     "flashv_model_create_rows", "flashv_model_rows_handle", "flashv_model_pull_rows", "flashv_model_pull_rows_from",
-    "flashv_model_finish", "flashv_shard_count", "flashv_decode_batch_shard",
+    "flashv_model_finish", "flashv_shard_count", "flashv_decode_batch_shard", "flashv_bs_decode_batch_shard",
     "flashv_mgpu_create", "flashv_mgpu_destroy", "flashv_mgpu_world", "flashv_mgpu_ctx", "flashv_mgpu_model",
-    "flashv_mgpu_model_create", "flashv_mgpu_decode_batch", "flashv_mgpu_decode",
+    "flashv_mgpu_model_create", "flashv_mgpu_decode_batch", "flashv_mgpu_bs_decode_batch", "flashv_mgpu_decode",
     "flashv_read_floats_cached", "flashv_trellis_init", "flashv_trellis_step", "flashv_trellis_step_columns_dev", "flashv_bs_score_step", "flashv_bs_heap_replay",
     "flashv_task_list", "flashv_executed_steps", "flashv_memory_bytes", "flashv_bs_memory_bytes",
 ]
@@ -144,6 +144,8 @@ def lib():
     L.flashv_mgpu_model_create.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp]
     L.flashv_mgpu_decode_batch.argtypes = [vp, ip, C.c_int, C.c_int, C.c_int, ip, fp, rp]
     L.flashv_mgpu_decode.argtypes = [vp, ip, C.c_int, C.c_int, ip, fp, rp]
+    L.flashv_bs_decode_batch_shard.argtypes = [vp, ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, fp, rp]
+    L.flashv_mgpu_bs_decode_batch.argtypes = [vp, ip, C.c_int, C.c_int, C.c_int, C.c_int, ip, fp, rp]
     L.flashv_trellis_init.argtypes = [vp, C.c_int, C.c_int, fp]
     L.flashv_trellis_step.argtypes = [vp, fp, C.c_int, fp, ip, C.c_int]
     L.flashv_trellis_step_columns_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
@@ -312,7 +314,7 @@ class Model:
     def prep_ms(self):
         return lib().flashv_model_prep_ms(self._h)
 
-    def decode_batch_shard(self, obs, N, rank, world, paths=None, scores=None):
+    def decode_batch_shard(self, obs, N, rank, world, paths=None, scores=None, B=0):
         """This rank's share (rows rank, rank+world, ...) of obs[total][T], left in place in paths/scores."""
         obs = np.ascontiguousarray(obs, np.int32)
         total, T = obs.shape
@@ -321,7 +323,10 @@ class Model:
         if scores is None:
             scores = np.zeros(total, np.float32)
         rep = Report()
-        _check(lib().flashv_decode_batch_shard(self._h, _i(obs), total, T, N, rank, world, _i(paths), _f(scores), C.byref(rep)))
+        if B > 0:
+            _check(lib().flashv_bs_decode_batch_shard(self._h, _i(obs), total, T, N, B, rank, world, _i(paths), _f(scores), C.byref(rep)))
+        else:
+            _check(lib().flashv_decode_batch_shard(self._h, _i(obs), total, T, N, rank, world, _i(paths), _f(scores), C.byref(rep)))
         return paths, scores, rep
 
     def decode(self, ob, N):
@@ -492,13 +497,16 @@ class MultiGpu:
     def prep_ms(self, rank=0):
         return lib().flashv_model_prep_ms(lib().flashv_mgpu_model(self._h, rank))
 
-    def decode_batch(self, obs, N):
+    def decode_batch(self, obs, N, B=0):
         obs = np.ascontiguousarray(obs, np.int32)
         batch, T = obs.shape
         paths = np.empty((batch, T), np.int32)
         scores = np.empty(batch, np.float32)
         rep = Report()
-        _check(lib().flashv_mgpu_decode_batch(self._h, _i(obs), batch, T, N, _i(paths), _f(scores), C.byref(rep)))
+        if B > 0:
+            _check(lib().flashv_mgpu_bs_decode_batch(self._h, _i(obs), batch, T, N, B, _i(paths), _f(scores), C.byref(rep)))
+        else:
+            _check(lib().flashv_mgpu_decode_batch(self._h, _i(obs), batch, T, N, _i(paths), _f(scores), C.byref(rep)))
         return paths, scores, rep
 
     def decode(self, ob, N):

@@ -24,8 +24,8 @@ extern "C" int flashv_shard_count(int total, int rank, int world)
     return total > rank ? (total - rank + world - 1) / world : 0;
 }
 
-extern "C" int flashv_decode_batch_shard(flashv_model *m, const int32_t *ob, int total, int T, int N, int rank, int world,
-                                         int32_t *path_out, float *score_out, flashv_report *report)
+static int batch_shard(flashv_model *m, const int32_t *ob, int total, int T, int N, int B, int rank, int world, int32_t *path_out,
+                       float *score_out, flashv_report *report)
 {
     const int mine = flashv_shard_count(total, rank, world);
     if (!m || !ob || !path_out || mine < 0 || T < 1) {
@@ -38,7 +38,8 @@ extern "C" int flashv_decode_batch_shard(flashv_model *m, const int32_t *ob, int
     std::vector<int32_t> lob((size_t)mine * T), lpath((size_t)mine * T);
     std::vector<float> lscore((size_t)mine);
     for (int q = 0; q < mine; ++q) memcpy(&lob[(size_t)q * T], ob + ((size_t)rank + (size_t)q * world) * T, (size_t)T * 4);
-    int rc = flashv_decode_batch(m, lob.data(), mine, T, N, lpath.data(), lscore.data(), report);
+    int rc = B > 0 ? flashv_bs_decode_batch(m, lob.data(), mine, T, N, B, lpath.data(), lscore.data(), report)
+                   : flashv_decode_batch(m, lob.data(), mine, T, N, lpath.data(), lscore.data(), report);
     if (rc != FLASHV_OK) return rc;
     for (int q = 0; q < mine; ++q) {
         const size_t b = (size_t)rank + (size_t)q * world;
@@ -46,6 +47,22 @@ extern "C" int flashv_decode_batch_shard(flashv_model *m, const int32_t *ob, int
         if (score_out) score_out[b] = lscore[q];
     }
     return FLASHV_OK;
+}
+
+extern "C" int flashv_decode_batch_shard(flashv_model *m, const int32_t *ob, int total, int T, int N, int rank, int world,
+                                         int32_t *path_out, float *score_out, flashv_report *report)
+{
+    return batch_shard(m, ob, total, T, N, 0, rank, world, path_out, score_out, report);
+}
+
+extern "C" int flashv_bs_decode_batch_shard(flashv_model *m, const int32_t *ob, int total, int T, int N, int B, int rank, int world,
+                                            int32_t *path_out, float *score_out, flashv_report *report)
+{
+    if (B < 1) {
+        set_error("flashv_bs_decode_batch_shard: BeamSearchWidth must be >= 1");
+        return FLASHV_ERR_ARG;
+    }
+    return batch_shard(m, ob, total, T, N, B, rank, world, path_out, score_out, report);
 }
 
 // ---- one process, all GPUs -------------------------------------------------------------------------
@@ -188,8 +205,8 @@ static void merge_report(flashv_report *into, const flashv_report &r, bool first
     into->kernel_launches += r.kernel_launches;
 }
 
-extern "C" int flashv_mgpu_decode_batch(flashv_mgpu *g, const int32_t *ob, int batch, int T, int N, int32_t *path_out,
-                                        float *score_out, flashv_report *report)
+static int mgpu_batch(flashv_mgpu *g, const int32_t *ob, int batch, int T, int N, int B, int32_t *path_out, float *score_out,
+                      flashv_report *report)
 {
     if (!g || !ob || !path_out || batch < 1 || g->model.empty() || !g->model[0]) {
         set_error("flashv_mgpu_decode_batch: bad argument, or no model (flashv_mgpu_model_create first)");
@@ -198,7 +215,7 @@ extern "C" int flashv_mgpu_decode_batch(flashv_mgpu *g, const int32_t *ob, int b
     const int W = (int)g->devices.size();
     std::vector<flashv_report> reps((size_t)W);
     int rc = for_each_device(
-        g, [&](int r) { return flashv_decode_batch_shard(g->model[r], ob, batch, T, N, r, W, path_out, score_out, &reps[r]); });
+        g, [&](int r) { return batch_shard(g->model[r], ob, batch, T, N, B, r, W, path_out, score_out, &reps[r]); });
     if (rc != FLASHV_OK) return rc;
     if (report) {
         bool first = true;
@@ -206,6 +223,22 @@ extern "C" int flashv_mgpu_decode_batch(flashv_mgpu *g, const int32_t *ob, int b
             if (flashv_shard_count(batch, r, W) > 0) merge_report(report, reps[r], first), first = false;
     }
     return FLASHV_OK;
+}
+
+extern "C" int flashv_mgpu_decode_batch(flashv_mgpu *g, const int32_t *ob, int batch, int T, int N, int32_t *path_out,
+                                        float *score_out, flashv_report *report)
+{
+    return mgpu_batch(g, ob, batch, T, N, 0, path_out, score_out, report);
+}
+
+extern "C" int flashv_mgpu_bs_decode_batch(flashv_mgpu *g, const int32_t *ob, int batch, int T, int N, int B, int32_t *path_out,
+                                           float *score_out, flashv_report *report)
+{
+    if (B < 1) {
+        set_error("flashv_mgpu_bs_decode_batch: BeamSearchWidth must be >= 1");
+        return FLASHV_ERR_ARG;
+    }
+    return mgpu_batch(g, ob, batch, T, N, B, path_out, score_out, report);
 }
 
 static int sharded_plans(flashv_mgpu *g, int T, int N, ShardedPlanSet **out)

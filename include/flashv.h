@@ -148,6 +148,9 @@ int flashv_shard_count(int total, int rank, int world);
  * has (MPI, torch.distributed, shared memory) — or uses flashv_mgpu_decode_batch inside one process. */
 int flashv_decode_batch_shard(flashv_model *model, const int32_t *ob, int total, int T, int N, int rank, int world,
                               int32_t *path_out, float *score_out, flashv_report *report);
+/* The same for FLASH-BS (S:548-577 per sequence); a single FLASH-BS sequence does not shard (replicas only). */
+int flashv_bs_decode_batch_shard(flashv_model *model, const int32_t *ob, int total, int T, int N, int B, int rank, int world,
+                                 int32_t *path_out, float *score_out, flashv_report *report);
 
 /* ---- state sharding of one huge K across the GPUs of a box -------------------- */
 /* Every rank holds the full model and an identical FLASH plan (batch 1, persistent engine).  After
@@ -183,6 +186,8 @@ int flashv_mgpu_model_create(flashv_mgpu *g, int K, int M, const float *A, const
  * report: decode_ms = the slowest device's. */
 int flashv_mgpu_decode_batch(flashv_mgpu *g, const int32_t *ob, int batch, int T, int N, int32_t *path_out,
                              float *score_out, flashv_report *report);
+int flashv_mgpu_bs_decode_batch(flashv_mgpu *g, const int32_t *ob, int batch, int T, int N, int B, int32_t *path_out,
+                                float *score_out, flashv_report *report);
 /* One sequence over a K too large for one GPU to be fast: pass 0 state-sharded, tree levels spread (above). */
 int flashv_mgpu_decode(flashv_mgpu *g, const int32_t *ob, int T, int N, int32_t *path_out, float *score_out,
                        flashv_report *report);

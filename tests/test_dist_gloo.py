@@ -61,3 +61,48 @@ def test_sequences_shard_over_two_ranks():
         mp.spawn(_worker, args=(2, port, obs, 3, ret), nprocs=2, join=True)
         assert np.array_equal(ret["paths"], want)
         assert ret["slowest"] == 2.0
+
+
+def _ctrl_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, str(ROOT / "tools"))
+        import bench_side
+        import gen_hmm
+
+        ctrl = bench_side.Ctrl(dist, rank, world)
+        got = ctrl.gather_objects(("rank", rank))
+        bc = ctrl.bcast_object({"x": 7} if rank == 0 else None)
+        slowest = ctrl.fmax(10.0 - rank)
+        agree = (ctrl.all_true(True), ctrl.all_true(rank == 0))
+        # the HMM of config 5 at toy size: rank 0 writes it into /dev/shm, every rank maps the same bytes
+        K, prob, seed = 40, 0.3, 4242 + os.getppid() % 1000
+        A, gen_s = bench_side.shared_hmm(ctrl, K, prob, seed)
+        want = gen_hmm.as_reference_floats(gen_hmm.transition_matrix(K, prob, seed))
+        same = bool(np.array_equal(np.asarray(A), want))
+        ctrl.barrier()
+        if rank == 0:
+            for suffix in ("", ".ok"):
+                try:
+                    os.unlink(f"/dev/shm/flashv_hmm_K{K}_p{prob}_s{seed}.f32{suffix}")
+                except OSError:
+                    pass
+        ret[rank] = (got, bc, slowest, agree, same, gen_s > 0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_control_plane_two_ranks():
+    """tools/bench_side.py's control plane (what bench.py --gpus N uses beside the data path: handle exchange,
+    flags, max-over-ranks times) and the shared-memory HMM of config 5, on two gloo ranks without a GPU."""
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        port = 29900 + (os.getpid() % 2000)
+        mp.spawn(_ctrl_worker, args=(2, port, ret), nprocs=2, join=True)
+        for rank in (0, 1):
+            got, bc, slowest, agree, same, generated = ret[rank]
+            assert got == [("rank", 0), ("rank", 1)] and bc == {"x": 7} and slowest == 10.0
+            assert agree == (True, False) and same
+            assert generated == (rank == 0)

@@ -86,6 +86,10 @@ def test_one_process_all_gpus(fv, oracle_mod):
             assert np.array_equal(paths[b], want), (N, b)
             assert _bits(scores[b]) == _bits(wscore)
         assert rep.kernel_launches > 0
+    paths, scores, _ = g.decode_batch(obs, 3, B=9)  # FLASH-BS batches shard the same way
+    for b in range(len(obs)):
+        want, wscore, _ = om.flash_bs(obs[b], 3, 9)
+        assert np.array_equal(paths[b], want) and _bits(scores[b]) == _bits(wscore), b
     for N in (5, 2):
         path, score, rep = g.decode(obs[0], N)
         want, wscore, _ = om.flash(obs[0], N)
