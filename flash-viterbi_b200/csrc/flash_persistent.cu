@@ -579,6 +579,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                         }
                     }
                 }
+                } else if (TM && a.pinned) {
+                    // pinned: the rest of the slice sits in shared memory, packed chunk after chunk.  Four 128-state
+                    // iterations per trip, all twelve loads requested before the 96 FP instructions that use them —
+                    // the same shape as the tensor-memory part above.  (One stage at a time, 6 loads then 48 FP
+                    // instructions, left this phase at 2.3-2.9 us against 0.8-1.8 us for the tensor-memory part.)
+                    if (s == 1)
+                        for (int u = nk_res; u < nk; ++u) mbar_wait(&full[u - nk_res], 0);
+                    if (have0) {
+                        const float4 *base4 = reinterpret_cast<const float4 *>(ring) + lane;
+                        const int n_it = (a.Kp - nk_res * TILE_CH) >> 7;  // 128-state iterations in shared memory
+                        const int rs0 = have0 ? rr0 : 0, rs1 = have1 ? rr1 : rs0;
+                        auto it_ptr = [&](int it, int row) -> const float4 * {
+                            const int c = it >> 1;  // chunk (TILE_CH = 256 states = two iterations); the last one may be shorter
+                            const int len4 = min(TILE_CH, a.Kp - (nk_res + c) * TILE_CH) >> 2;
+                            return base4 + (size_t)c * ncr * (TILE_CH >> 2) + row * len4 + (it & 1) * 32;
+                        };
+                        int it = 0;
+#pragma unroll 1
+                        for (; it + 4 <= n_it; it += 4) {
+                            float4 ha[4], hb[4], dd[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                ha[e] = *it_ptr(it + e, rs0);
+                                hb[e] = *it_ptr(it + e, rs1);
+                                dd[e] = dring[(it + e) * 32];
+                            }
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { FV_ACC2(dd[e], ha[e], hb[e]) }
+                        }
+                        for (; it < n_it; ++it) {
+                            const float4 d = dring[it * 32];
+                            const float4 h0 = *it_ptr(it, rs0);
+                            const float4 h1 = *it_ptr(it, rs1);
+                            FV_ACC2(d, h0, h1)
+                        }
+                    }
                 } else if (TM || ph == 0) {
                     for (int u = nk_res; u < nk; ++u) {
                     const float4 *stage4 = reinterpret_cast<const float4 *>(
@@ -614,6 +650,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                     }
                 }
                 }
+                if (tracing && ph == 0) tr[6] = clock64();  // between the two operand phases (tensor memory / shared memory, in the warp's order)
             }
             if (tracing) tr[2] = clock64();
             if (!have0) continue;  // warp-uniform

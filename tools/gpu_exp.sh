@@ -1,9 +1,11 @@
 #!/bin/bash
-# scratch script for the experiment at hand: pipelined heap replay in FLASH-BS
+# scratch script for the experiment at hand: batched loads in the pinned shared-memory phase of the persistent pass
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_multi_gpu.py tests/test_host_programs.py -m gpu -q -x --timeout 600 -p no:cacheprovider -k "bs or golden or one_process or host_program or dag" > gpurun_out/pytest_res.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 -p no:cacheprovider -k "trellis_step or goldens or golden_vectors or bench_instance_flash or random_models or wide_model or headline_flash_vs" > gpurun_out/pytest_res.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_res.log
 tail -3 gpurun_out/pytest_res.log
-FLASHV_BS_TRACE=1 python tools/profile_target.py --beam 128 --segments 8 --iters 3 2>&1 | grep "steps=255\|engine" | tail -2
-python tools/profile_target.py --beam 128 --segments 127 --iters 3
-FLASHV_BS_TRACE=1 python tools/profile_target.py --beam 32 --segments 1 --iters 3 2>&1 | grep "steps=255\|engine" | tail -2
+python tools/profile_target.py --engine persistent --segments 127 --iters 6
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-extras > gpurun_out/bench_a.log 2> gpurun_out/bench_a.err
+python tools/summarize_bench.py gpurun_out/bench_a.log | head -3
+FLASHV_TRACE_FILE=gpurun_out/trace.bin python tools/profile_target.py --engine persistent --segments 127 --iters 3 > gpurun_out/trace_run.log 2>&1
+python tools/trace_report.py gpurun_out/trace.bin 2>&1

@@ -18,8 +18,10 @@ for w, wn in enumerate(["warp 0", "last warp"]):
         b_ = t[sel, :, w, 2] - t[sel, :, w, 6]
         ok = (t[sel, :, w, 6] > 0) & (t[sel, :, w, 2] > 0)
         if ok.any():
-            print(f"   {'  resident part':20s} mean {us(a_[ok].mean()):7.2f} us")
-            print(f"   {'  ring part':20s} mean {us(b_[ok].mean()):7.2f} us")
+            # even warps take the tensor-memory chunks first, odd warps (the last one) the shared-memory ones
+            first, second = ("tensor memory", "shared memory") if w == 0 else ("shared memory", "tensor memory")
+            print(f"   {'  1st: ' + first:20s} mean {us(a_[ok].mean()):7.2f} us")
+            print(f"   {'  2nd: ' + second:20s} mean {us(b_[ok].mean()):7.2f} us")
     for p in range(5):
         d = t[sel, :, w, p + 1] - t[sel, :, w, p]
         ok = (t[sel, :, w, p + 1] > 0) & (t[sel, :, w, p] > 0)
