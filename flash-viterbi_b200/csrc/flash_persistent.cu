@@ -183,6 +183,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float4 (&ha)[4], float
 struct PersistArgs {
     const float *hiC;  // CTA-tiled (float)log A of the columns [col_begin, col_begin+ncol), tile_geom.h
     int col_begin, ncol;  // destination columns this GPU owns (all of them unless the pass is state-sharded)
+    const double *LAc;  // chain-major double table of models up to 4096 states (tables.cu), else null
     const double *LAd;
     const float *LBf;
     int K, Kp;
@@ -236,6 +237,7 @@ __device__ __forceinline__ void publish_delta_peers(const PersistArgs &a, int pa
 {
     const unsigned long long w = ((unsigned long long)step_tag(a, step) << 32) | (unsigned long long)__float_as_uint(v);
     if (last) __threadfence_system();
+#pragma unroll 1
     for (int r = 0; r < a.npeer; ++r)
         asm volatile("st.global.u64 [%0], %1;" ::"l"(a.xch_peer[r] + (size_t)parity * a.Kp + i), "l"(w) : "memory");
 }
@@ -298,110 +300,79 @@ __device__ __forceinline__ void delta_wait_load(const PersistArgs &a, int s, flo
     named_bar_sync(1, NCONS);
 }
 
-// Candidates of one column inside the window, gathered lane-locally: the newest candidate's double
-// load stays in flight (`la`), older ones of the same lane are folded into `acc` on arrival.
-struct Pending {
-    Best acc;
-    double la;
-    float pre;
-    int k;
-    bool has;
-};
-
-__device__ __forceinline__ void pending_push(Pending &p, float pre, int k, const double *__restrict__ la_ptr)
-{
-    if (p.has) {
-        const float x = exact_cand(p.pre, p.la);
-        if (x > -FLT_MAX) best_take(p.acc, x, p.k);
-    }
-    p.pre = pre, p.k = k, p.la = __ldg(la_ptr), p.has = true;
-}
-
-__device__ __forceinline__ Best pending_finish(Pending &p)
-{
-    if (p.has) {
-        const float x = exact_cand(p.pre, p.la);
-        if (x > -FLT_MAX) best_take(p.acc, x, p.k);
-    }
-    Best b = warp_best(p.acc);
-    if (!(b.x > -FLT_MAX)) b.x = -FLT_MAX, b.k = -1;
-    return b;
-}
-
-// Window scan of one column, split in two so that the L2 reads of several columns overlap:
-// scan_fetch() finds the chains whose maximum lies inside the window and loads, per lane, the
-// estimate inputs of (up to) SCAN_SLOTS chain elements from the tiled table; scan_commit() compares
-// them against the window and starts the exact double loads.  Anything that does not fit the slots
-// (several chains inside the window, or chains longer than 32 elements) takes the slow path
-// inside scan_commit(), which re-reads synchronously.
+// Window scan of one column.  The sweep leaves every lane with the float-estimate maxima of four "chains":
+// chain q = k & 127 holds the source states k = q + 128 u, u = 0 .. Kp/128 - 1 (lane w, accumulator c  <->
+// q = 4 w + c).  The winner can only sit in a chain whose maximum lies inside the window (WINDOW_STEPS float
+// steps below the column's best estimate), which is one chain in almost every column, sometimes two.
+//
+// For K <= 4096 a chain has at most 32 elements and the model carries the chain-major double table LAc
+// (tables.cu): LAc[(i * 128 + q) * 32 + u] = log A[q + 128 u][i], -inf beyond K.  scan_fetch() has lane u
+// load element u of each chain inside the window — ONE coalesced 256-byte request per chain and column —
+// and scan_settle() derives both the float estimate ((float)la, the very number the sweep used) and the exact
+// candidate from it.  (Before the chain table the estimates were re-read from the tiled float table, 31
+// different lines per chain, and the doubles of the survivors fetched from LAd afterwards: two dependent
+// round trips, the first of them 31 requests wide.  See profiles/README.md, round 2.)
+//
+// Columns with more chains inside the window than SCAN_SLOTS, and all columns of wider models, go through
+// scan_slow(), which walks the chains synchronously.
 constexpr int SCAN_SLOTS = 2;
+constexpr int CHAIN_PAD = 32;  // elements per chain in LAc
 struct Scan {
-    float hi0, hi1;  // slot s holds element `lane` of the s-th chain inside the window
-    int k0, k1;      // its source state, or -1 if this lane has no element in that slot
-    int thr;         // window threshold (ordinal), warp-uniform
-    unsigned overflow;  // warp-uniform: some chain did not fit the slots
-    bool dead;       // warp-uniform: no finite estimate in the column
+    double la0, la1;    // slot s holds element `lane` of the s-th chain inside the window
+    int k0, k1;         // its source state, or -1 if this lane has no element in that slot
+    int thr;            // window threshold (ordinal), warp-uniform
+    unsigned overflow;  // warp-uniform: the column goes through scan_slow()
+    bool dead;          // warp-uniform: no finite estimate in the column
 };
 
-__device__ __forceinline__ void scan_fetch(Scan &sc, const float (&cm)[4], const float *__restrict__ round_base,
-                                           int ncr, int rr, int K, int Kp, int lane)
+__device__ __forceinline__ void scan_fetch(Scan &sc, const float (&cm)[4], const double *__restrict__ LAc, int i, int K,
+                                           int Kp, int lane)
 {
-    sc.k0 = sc.k1 = -1, sc.hi0 = sc.hi1 = 0.f, sc.overflow = 0;
+    sc.k0 = sc.k1 = -1, sc.la0 = sc.la1 = 0.0, sc.overflow = 0;
     const float top = warp_max(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
     sc.dead = !(top > -FLT_MAX);
     sc.thr = ford(top) - WINDOW_STEPS;
     if (sc.dead) return;
-    const int chain_len = Kp >> 7;
+    // the four ballots first, then ONE loop over whatever they found: the loop body exists once, which keeps
+    // this latency-bound stretch of the step short in the instruction cache
+    unsigned h0 = __ballot_sync(FULL_MASK, ford(cm[0]) >= sc.thr), h1 = __ballot_sync(FULL_MASK, ford(cm[1]) >= sc.thr);
+    unsigned h2 = __ballot_sync(FULL_MASK, ford(cm[2]) >= sc.thr), h3 = __ballot_sync(FULL_MASK, ford(cm[3]) >= sc.thr);
+    if (LAc == nullptr || __popc(h0) + __popc(h1) + __popc(h2) + __popc(h3) > SCAN_SLOTS) {
+        sc.overflow = 1;
+        return;
+    }
+    const double *col = LAc + (size_t)i * (128 * CHAIN_PAD) + lane;
     int used = 0;  // warp-uniform count of chains taken
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        unsigned hit = __ballot_sync(FULL_MASK, ford(cm[c]) >= sc.thr);
-        while (hit) {
-            const int w = __ffs(hit) - 1;
-            hit &= hit - 1;
-            if (used >= SCAN_SLOTS || chain_len > 32) {
-                sc.overflow = 1;
-                continue;
-            }
-            const int k = 4 * (w + 32 * lane) + c;  // element `lane` of chain (w, c)
-            // `used` is warp-uniform: branch, so that the load lands in its slot without being
-            // consumed (a select on the loaded value would wait for it right here)
-            const bool mine = lane < chain_len && k < K;
-            const float *src = round_base + tile_round_off(Kp, ncr, rr, mine ? k : 0);
-            if (used == 0) {
-                if (mine) sc.k0 = k, sc.hi0 = __ldg(src);
-            } else {
-                if (mine) sc.k1 = k, sc.hi1 = __ldg(src);
-            }
-            ++used;
-        }
+#pragma unroll 1
+    while (h0 | h1 | h2 | h3) {
+        const int c = h0 ? 0 : h1 ? 1 : h2 ? 2 : 3;
+        const unsigned hc = h0 ? h0 : h1 ? h1 : h2 ? h2 : h3;
+        const int q = 4 * (__ffs(hc) - 1) + c;
+        if (h0) h0 &= h0 - 1;
+        else if (h1) h1 &= h1 - 1;
+        else if (h2) h2 &= h2 - 1;
+        else h3 &= h3 - 1;
+        const int k = q + 128 * lane;  // element `lane` of chain q; the table pads with -inf, so every lane may load
+        // `used` is warp-uniform: branch, so that the load lands in its slot without being consumed
+        if (used == 0) sc.k0 = k, sc.la0 = __ldg(col + q * CHAIN_PAD);
+        else sc.k1 = k, sc.la1 = __ldg(col + q * CHAIN_PAD);
+        ++used;
     }
 }
 
-__device__ __forceinline__ void scan_commit(Pending &p, const Scan &sc, const float (&cm)[4], float tmp,
-                                            const float *__restrict__ round_base, int ncr, int rr, const float *sdelta,
-                                            const double *__restrict__ LAd, int K, int Kp, int i, int lane)
+// The rare column that does not fit the slots (and every column of a model wider than 4096 states): every
+// chain inside the window, element by element, estimates from the tiled float table, each exact value loaded
+// on the spot.  Kept out of line: inlined twice per step it only stretched the code the common path fetches.
+__device__ __noinline__ Best scan_slow(float cm0, float cm1, float cm2, float cm3, int thr, float tmp,
+                                       const float *__restrict__ round_base, int ncr, int rr, const float *sdelta,
+                                       const double *__restrict__ LAd, int K, int Kp, int i, int lane)
 {
-    p.acc = Best{-FLT_MAX, 0x7fffffff};
-    p.has = false;
-    p.la = 0.0, p.pre = 0.f, p.k = 0;
-    if (sc.dead) return;
-    if (!sc.overflow) {
-        if (sc.k0 >= 0) {
-            const float pre = __fadd_rn(tmp, sdelta[sc.k0]);
-            if (ford(__fadd_rn(pre, sc.hi0)) >= sc.thr) pending_push(p, pre, sc.k0, LAd + (size_t)sc.k0 * K + i);
-        }
-        if (sc.k1 >= 0) {
-            const float pre = __fadd_rn(tmp, sdelta[sc.k1]);
-            if (ford(__fadd_rn(pre, sc.hi1)) >= sc.thr) pending_push(p, pre, sc.k1, LAd + (size_t)sc.k1 * K + i);
-        }
-        return;
-    }
-    // slow path: every chain inside the window, element by element
+    Best acc{-FLT_MAX, 0x7fffffff};
     const int chain_len = Kp >> 7;
+    const float cm[4] = {cm0, cm1, cm2, cm3};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        unsigned hit = __ballot_sync(FULL_MASK, ford(cm[c]) >= sc.thr);
+        unsigned hit = __ballot_sync(FULL_MASK, ford(cm[c]) >= thr);
         while (hit) {
             const int w = __ffs(hit) - 1;
             hit &= hit - 1;
@@ -410,17 +381,57 @@ __device__ __forceinline__ void scan_commit(Pending &p, const Scan &sc, const fl
                 if (k < K) {
                     const float pre = __fadd_rn(tmp, sdelta[k]);
                     const float est = __fadd_rn(pre, __ldg(round_base + tile_round_off(Kp, ncr, rr, k)));
-                    if (ford(est) >= sc.thr) pending_push(p, pre, k, LAd + (size_t)k * K + i);
+                    if (ford(est) >= thr) {
+                        const float x = exact_cand(pre, __ldg(LAd + (size_t)k * K + i));
+                        if (x > -FLT_MAX) best_take(acc, x, k);
+                    }
                 }
             }
         }
     }
+    return acc;
+}
+
+// The column's winner: exact candidates of everything inside the window, best of the warp.
+__device__ __forceinline__ Best scan_settle(const Scan &sc, const float (&cm)[4], float tmp,
+                                            const float *__restrict__ round_base, int ncr, int rr, const float *sdelta,
+                                            const double *__restrict__ LAd, int K, int Kp, int i, int lane)
+{
+    Best acc{-FLT_MAX, 0x7fffffff};
+    if (!sc.dead) {
+        if (sc.overflow) {
+            acc = scan_slow(cm[0], cm[1], cm[2], cm[3], sc.thr, tmp, round_base, ncr, rr, sdelta, LAd, K, Kp, i, lane);
+        } else {
+            if (sc.k0 >= 0 && sc.k0 < K) {
+                const float pre = __fadd_rn(tmp, sdelta[sc.k0]);
+                if (ford(__fadd_rn(pre, __double2float_rn(sc.la0))) >= sc.thr) {
+                    const float x = exact_cand(pre, sc.la0);
+                    if (x > -FLT_MAX) best_take(acc, x, sc.k0);
+                }
+            }
+            if (sc.k1 >= 0 && sc.k1 < K) {
+                const float pre = __fadd_rn(tmp, sdelta[sc.k1]);
+                if (ford(__fadd_rn(pre, __double2float_rn(sc.la1))) >= sc.thr) {
+                    const float x = exact_cand(pre, sc.la1);
+                    if (x > -FLT_MAX) best_take(acc, x, sc.k1);
+                }
+            }
+        }
+    }
+    Best b = warp_best(acc);
+    if (!(b.x > -FLT_MAX)) b.x = -FLT_MAX, b.k = -1;
+    return b;
 }
 
 // TM: the first TM_RES_CHUNKS chunks of every owned column live in tensor memory (single-round CTAs only).
-template <bool TM>
+// PIN (needs TM): the rest of the CTA's slice fits shared memory and is loaded once (a.pinned).
+// PEERS: state-sharded pass, results go to every GPU (a.npeer > 1).
+// Compile-time switches rather than the fields of `a`: the step loop is latency-bound and branchy, and
+// every variant it does not need is code its instruction fetch has to step over.
+template <bool TM, bool PIN, bool PEERS>
 __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs a)
 {
+    static_assert(TM || !PIN, "the pinned ring is a tensor-memory mode");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Kp4 = a.Kp >> 2;
     const int nk = (a.Kp + TILE_CH - 1) / TILE_CH;  // chunks per column
@@ -451,7 +462,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
 
     if (warp == NCW) {
         // ---------------- producer: the slab, once per step, linearly through the ring -----------
-        if (lane == 0 && a.pinned) {
+        if (PIN && lane == 0) {
             // the whole streamed part fits: one copy per chunk, packed back to back exactly as the table stores
             // them (the last chunk may be shorter), each with its own barrier; nothing is ever refilled
             const unsigned char *src = reinterpret_cast<const unsigned char *>(slab) + (size_t)nk_res * TILE_CH * ncols * sizeof(float);
@@ -463,7 +474,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                 off += bytes;
             }
         }
-        if (a.pinned) {
+        if (PIN) {
             // nothing to stream: the producer warp is done (prefetching this CTA's columns of the double table
             // into L2 here was tried — 125.8 MB against 126 MB of L2 — and changed nothing: 2.10 ms against 2.09)
         } else if (lane == 0) {
@@ -510,12 +521,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
     int st = 0;           // every consumer warp visits every ring item, in the producer's order
     uint32_t parity = 0;  // parity of the ring wrap count = phase parity to wait for
     const int nk_full = a.Kp / TILE_CH;  // chunks of exactly TILE_CH states; at most one shorter chunk follows
+    // The emission terms of a step hang off a two-load chain (observation -> row of log B -> entry) that has
+    // nothing to do with the delta hand-over, so it runs ahead of it: the observation one step early, the
+    // entries of the first round before the poll.
+    int ob_next = __ldg(a.ob + a.L + 1);
+    const int pre_i0 = a.col_begin + c0 + min(warp * CPW, max(ncols - 1, 0));
+    const int pre_i1 = a.col_begin + c0 + min(warp * CPW + 1, max(ncols - 1, 0));
     for (int s = 1; s <= a.nsteps; ++s) {
         unsigned long long *xout = a.xch + (size_t)(s & 1) * a.Kp;
         const bool last_step = s == a.nsteps;
         const int j = a.L + s;
-        const float *tmp_row = a.LBf + (size_t)__ldg(a.ob + j) * a.Kp;  // F:167
-        const bool keep = j >= a.mid + 1;                                // F:242
+        const float *tmp_row = a.LBf + (size_t)ob_next * a.Kp;  // F:167
+        const float pre_tmp0 = __ldg(tmp_row + pre_i0), pre_tmp1 = __ldg(tmp_row + pre_i1);
+        if (!last_step) ob_next = __ldg(a.ob + j + 1);
+        const bool keep = j >= a.mid + 1;                        // F:242
         const bool tracing = a.trace != nullptr && s <= TRACE_STEPS && lane == 0 && (warp == 0 || warp == NCW - 1);
         long long *tr = tracing ? a.trace + ((((size_t)(s - 1) * G + b) * 2 + (warp == 0 ? 0 : 1)) * TRACE_PTS) : nullptr;
         if (tracing) tr[0] = clock64();
@@ -528,7 +547,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             const bool have0 = rr0 < ncr, have1 = rr1 < ncr;
             const int i0 = a.col_begin + c0 + rho * TILE_RW + (have0 ? rr0 : 0);  // global state indices
             const int i1 = a.col_begin + c0 + rho * TILE_RW + (have1 ? rr1 : 0);
-            const float tmp0 = __ldg(tmp_row + i0), tmp1 = __ldg(tmp_row + i1);
+            // a missing column stands in as the CTA's last one in the preloaded pair, as its first one here: either way unused
+            const float tmp0 = rho == 0 && have0 ? pre_tmp0 : __ldg(tmp_row + i0);
+            const float tmp1 = rho == 0 && have1 ? pre_tmp1 : __ldg(tmp_row + i1);
             float cm0[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             float cm1[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             // row offsets inside a full stage, in float4 units; a duplicate row stands in for a missing one
@@ -550,6 +571,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             // holds (almost) a whole step of streamed chunks, so the order does not stall the producer.
             const bool ring_first = TM && (warp & 1);
             const float4 *dring = d4 + nk_res * (TILE_CH >> 2);
+#pragma unroll 1
             for (int ph = 0; ph < 2; ++ph) {
                 const bool tm_now = TM && ((ph == 0) != ring_first);
                 if (tm_now) {
@@ -579,7 +601,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                         }
                     }
                 }
-                } else if (TM && a.pinned) {
+                } else if (PIN) {
                     // pinned: the rest of the slice sits in shared memory, packed chunk after chunk.  Four 128-state
                     // iterations per trip, all twelve loads requested before the 96 FP instructions that use them —
                     // the same shape as the tensor-memory part above.  (One stage at a time, 6 loads then 48 FP
@@ -617,10 +639,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                     }
                 } else if (TM || ph == 0) {
                     for (int u = nk_res; u < nk; ++u) {
-                    const float4 *stage4 = reinterpret_cast<const float4 *>(
-                        a.pinned ? ring + (size_t)(u - nk_res) * ncr * TILE_CH * sizeof(float) : ring + (size_t)st * STAGE_BYTES);
-                    if (!a.pinned) mbar_wait(&full[st], parity);
-                    else if (s == 1) mbar_wait(&full[u - nk_res], 0);
+                    const float4 *stage4 = reinterpret_cast<const float4 *>(ring + (size_t)st * STAGE_BYTES);
+                    mbar_wait(&full[st], parity);
                     if (have0) {
                         if (u < nk_full) {
 #pragma unroll
@@ -643,11 +663,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                         }
                     }
                     dring += TILE_CH >> 2;
-                    if (!a.pinned) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty[st]);
-                        if (++st == a.nstage) st = 0, parity ^= 1;
-                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[st]);
+                    if (++st == a.nstage) st = 0, parity ^= 1;
                 }
                 }
                 if (tracing && ph == 0) tr[6] = clock64();  // between the two operand phases (tensor memory / shared memory, in the warp's order)
@@ -655,17 +673,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             if (tracing) tr[2] = clock64();
             if (!have0) continue;  // warp-uniform
             const float *round_base = slab + (size_t)rho * TILE_RW * a.Kp;
-            Pending q0, q1;
             Scan s0, s1;
-            scan_fetch(s0, cm0, round_base, ncr, rr0, a.K, a.Kp, lane);
-            if (have1) scan_fetch(s1, cm1, round_base, ncr, rr1, a.K, a.Kp, lane);
-            scan_commit(q0, s0, cm0, tmp0, round_base, ncr, rr0, sdelta, a.LAd, a.K, a.Kp, i0, lane);
-            if (have1) scan_commit(q1, s1, cm1, tmp1, round_base, ncr, rr1, sdelta, a.LAd, a.K, a.Kp, i1, lane);
+            scan_fetch(s0, cm0, a.LAc, i0, a.K, a.Kp, lane);
+            if (have1) scan_fetch(s1, cm1, a.LAc, i1, a.K, a.Kp, lane);
             if (tracing) tr[3] = clock64();
-            const Best r0 = pending_finish(q0);
+            const Best r0 = scan_settle(s0, cm0, tmp0, round_base, ncr, rr0, sdelta, a.LAd, a.K, a.Kp, i0, lane);
             if (lane == 0) {
-                if (a.npeer > 1) {
+                if (PEERS) {
                     if (keep)
+#pragma unroll 1
                         for (int r = 0; r < a.npeer; ++r)
                             psi_store(a.psi_peer[r], a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i0, r0.k);
                     publish_delta_peers(a, s & 1, i0, r0.x, s, last_step);
@@ -676,10 +692,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                 }
             }
             if (have1) {
-                const Best r1 = pending_finish(q1);
+                const Best r1 = scan_settle(s1, cm1, tmp1, round_base, ncr, rr1, sdelta, a.LAd, a.K, a.Kp, i1, lane);
                 if (lane == 0) {
-                    if (a.npeer > 1) {
+                    if (PEERS) {
                         if (keep)
+#pragma unroll 1
                             for (int r = 0; r < a.npeer; ++r)
                                 psi_store(a.psi_peer[r], a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i1, r1.k);
                         publish_delta_peers(a, s & 1, i1, r1.x, s, last_step);
@@ -696,7 +713,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
         if (tracing) tr[5] = clock64();
     }
 #undef FV_ACC2
-    if (a.npeer > 1) {
+    if (PEERS) {
         // Final hand-shake of a sharded pass: wait until every GPU's last delta slice has arrived
         // here (their release stores order their backpointer entries before it), acquire, and
         // leave the complete final vector where k_flash_end expects it.
@@ -762,7 +779,10 @@ static int launch_persist(flashv_model *m, PersistArgs &a)
             smem = fixed + std::max(rest, (size_t)16);
         }
     }
-    const void *fn = use_tmem ? (const void *)k_flash_persist<true> : (const void *)k_flash_persist<false>;
+    const bool peers = a.npeer > 1;
+    const void *fn = a.pinned  ? (peers ? (const void *)k_flash_persist<true, true, true> : (const void *)k_flash_persist<true, true, false>)
+                     : use_tmem ? (peers ? (const void *)k_flash_persist<true, false, true> : (const void *)k_flash_persist<true, false, false>)
+                                : (peers ? (const void *)k_flash_persist<false, false, true> : (const void *)k_flash_persist<false, false, false>);
     FV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     FV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NTHREADS, smem));
@@ -810,7 +830,7 @@ int persistent_pass(flashv_plan *p, const Pass &pass)
     flashv_model *m = p->model;
     const VecDesc &vd = pass.first_vec;  // the pass has exactly one vector (batch == 1)
     PersistArgs a;
-    a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+    a.LAd = m->LAd, a.LAc = m->LAc, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.ob = p->d_ob;
     a.L = vd.L, a.nsteps = vd.R - vd.L, a.mid = vd.mid, a.psi_row = vd.psi_row;
     a.d_init = p->d_delta, a.d_final = p->d_delta + (size_t)p->max_vec * m->Kp;
@@ -928,7 +948,7 @@ int persistent_single_step(flashv_model *m, const float *d_in_dev, int o, float 
     FV_CUDA(cudaStreamSynchronize(ctx->stream));
     PersistArgs a;
     a.hiC = m->hiC, a.col_begin = 0, a.ncol = m->K, a.npeer = 1;
-    a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+    a.LAd = m->LAd, a.LAc = m->LAc, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.ob = dob, a.L = 0, a.nsteps = 1, a.mid = 0, a.psi_row = 0;
     static unsigned hook_epoch = 0;
     a.epoch = (++hook_epoch & 0xffffu) ? (hook_epoch & 0xffffu) : (++hook_epoch & 0xffffu);

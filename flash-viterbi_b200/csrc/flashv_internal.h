@@ -92,6 +92,7 @@ struct flashv_model {
     int Kp = 0;               // K rounded up to a multiple of 128 (one warp x float4)
     float *hiT = nullptr;     // [K][Kp]  (float)log A, destination-major: hiT[i][k] = log A[k][i]; pad = -inf
     float *hiC = nullptr;     // K*Kp     the same, CTA-tiled for the persistent engine (tile_geom.h)
+    double *LAc = nullptr;    // K*4096   log A chain-major for the persistent engine's window scan (K <= 4096 only)
     int *csc_ptr = nullptr;       // in-edge lists of the transition graph (flash_sparse.cu); null when the table is dense or K >= 65536
     uint16_t *csc_k = nullptr;
     double *csc_la = nullptr;

@@ -72,6 +72,17 @@ __global__ void k_build_source_major(const double *__restrict__ LAd, float *__re
     hiS[(size_t)k * Kp + i] = (k < K && i < K) ? __double2float_rn(LAd[(size_t)k * K + i]) : -INFINITY;
 }
 
+// LAc: the double table chain-major, for the persistent engine's window scan (flash_persistent.cu): chain
+// q = k & 127 of column i holds its up to 32 source states k = q + 128 u next to each other,
+// LAc[(i * 128 + q) * 32 + u], -inf beyond K — 32 KB per column, models up to 4096 states.
+__global__ void k_build_chains(const double *__restrict__ LAd, double *__restrict__ LAc, int K)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // coalesced reads along i, scattered 8-byte writes
+    const int k = blockIdx.y;                             // 0 .. 4095
+    if (i >= K) return;
+    LAc[((size_t)i * 128 + (k & 127)) * 32 + (k >> 7)] = k < K ? LAd[(size_t)k * K + i] : -INFINITY;
+}
+
 void build_tiled_slice(const double *LAd, float *hiC, int K, int Kp, int col_begin, int ncol, int G, cudaStream_t st)
 {
     k_build_tiled<<<dim3((ncol + 255) / 256, Kp), 256, 0, st>>>(LAd, hiC, K, Kp, col_begin, ncol, G);
@@ -240,6 +251,12 @@ int tables_layouts(flashv_model *m)
     m->tile_G = ctx->sm_count < K ? ctx->sm_count : K;
     build_tiled_slice(m->LAd, m->hiC, K, Kp, 0, K, m->tile_G, ctx->stream);
     FV_CUDA(cudaGetLastError());
+    if (Kp <= 4096) {
+        FV_CUDA(cudaMalloc(&m->LAc, (size_t)K * 4096 * sizeof(double)));
+        m->bytes += (size_t)K * 4096 * sizeof(double);
+        k_build_chains<<<dim3((K + 255) / 256, 4096), 256, 0, ctx->stream>>>(m->LAd, m->LAc, K);
+        FV_CUDA(cudaGetLastError());
+    }
     if (prep_trace()) {
         cudaStreamSynchronize(ctx->stream);
         fprintf(stderr, "[flashv prep] dense layouts: %.2f ms\n", ms_since(t0));
