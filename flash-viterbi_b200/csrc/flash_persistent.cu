@@ -329,9 +329,10 @@ __device__ __forceinline__ void scan_fetch(Scan &sc, const float (&cm)[4], const
                                            int Kp, int lane)
 {
     sc.k0 = sc.k1 = -1, sc.la0 = sc.la1 = 0.0, sc.overflow = 0;
-    const float top = warp_max(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
-    sc.dead = !(top > -FLT_MAX);
-    sc.thr = ford(top) - WINDOW_STEPS;
+    // the warp's maximum in ONE instruction (redux.sync on the monotone integer image) instead of five shuffle rounds
+    const int top = __reduce_max_sync(FULL_MASK, ford(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]))));
+    sc.dead = top <= ford(-FLT_MAX);
+    sc.thr = top - WINDOW_STEPS;
     if (sc.dead) return;
     // the four ballots first, then ONE loop over whatever they found: the loop body exists once, which keeps
     // this latency-bound stretch of the step short in the instruction cache
@@ -418,7 +419,14 @@ __device__ __forceinline__ Best scan_settle(const Scan &sc, const float (&cm)[4]
             }
         }
     }
-    Best b = warp_best(acc);
+    // best of the warp, "larger value, then smaller index", in two redux.sync instead of ten shuffles.  The value
+    // comes back out of its integer image; that turns a -0 into +0, which cannot occur here (a sum is -0 only if
+    // both terms are, and no logarithm is).
+    const int ox = ford(acc.x);
+    const int m = __reduce_max_sync(FULL_MASK, ox);
+    Best b;
+    b.k = __reduce_min_sync(FULL_MASK, ox == m ? acc.k : 0x7fffffff);
+    b.x = __int_as_float(m >= 0 ? m : (int)((unsigned)(-m) | 0x80000000u));
     if (!(b.x > -FLT_MAX)) b.x = -FLT_MAX, b.k = -1;
     return b;
 }
@@ -535,7 +543,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
         const float pre_tmp0 = __ldg(tmp_row + pre_i0), pre_tmp1 = __ldg(tmp_row + pre_i1);
         if (!last_step) ob_next = __ldg(a.ob + j + 1);
         const bool keep = j >= a.mid + 1;                        // F:242
-        const bool tracing = a.trace != nullptr && s <= TRACE_STEPS && lane == 0 && (warp == 0 || warp == NCW - 1);
+        const bool tracing = a.trace != nullptr && s <= TRACE_STEPS && lane == 0 && (warp == 0 || warp == 1);  // one warp of either phase order, both with two columns
         long long *tr = tracing ? a.trace + ((((size_t)(s - 1) * G + b) * 2 + (warp == 0 ? 0 : 1)) * TRACE_PTS) : nullptr;
         if (tracing) tr[0] = clock64();
         delta_wait_load(a, s, reinterpret_cast<float *>(sdelta4), tid);

@@ -1,14 +1,9 @@
 #!/bin/bash
-# scratch script for the experiment at hand: window scan from the chain-major double table
+# scratch script for the experiment at hand: redux.sync in the window scan
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 -p no:cacheprovider -k "trellis_step or goldens or golden_vectors or bench_instance_flash or random_models or wide_model or headline_flash_vs" > gpurun_out/pytest_res.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_res.log
 tail -3 gpurun_out/pytest_res.log
 python tools/profile_target.py --engine persistent --segments 127 --iters 6
-for K in 2048 3072; do
-python tools/profile_target.py --engine persistent --segments 127 --iters 6 --K $K
-done
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-extras > gpurun_out/bench_a.log 2> gpurun_out/bench_a.err
-python tools/summarize_bench.py gpurun_out/bench_a.log | head -3
 FLASHV_TRACE_FILE=gpurun_out/trace.bin python tools/profile_target.py --engine persistent --segments 127 --iters 3 > gpurun_out/trace_run.log 2>&1
 python tools/trace_report.py gpurun_out/trace.bin 2>&1

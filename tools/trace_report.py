@@ -11,7 +11,7 @@ mhz = float(sys.argv[2]) if len(sys.argv) > 2 else 1965.0
 us = lambda c: c / mhz
 names = ["poll+stage delta", "stream+compute", "scan+exact", "publish", "end barrier"]
 sel = slice(4, steps)  # skip the first steps (cold ring)
-for w, wn in enumerate(["warp 0", "last warp"]):
+for w, wn in enumerate(["warp 0", "warp 1"]):
     print(wn)
     if pts >= 7:  # point 6 sits between the tensor-memory part and the ring part of the stream phase
         a_ = t[sel, :, w, 6] - t[sel, :, w, 1]
