@@ -316,48 +316,44 @@ __device__ __forceinline__ void delta_wait_load(const PersistArgs &a, int s, flo
 // Columns with more chains inside the window than SCAN_SLOTS, and all columns of wider models, go through
 // scan_slow(), which walks the chains synchronously.
 constexpr int SCAN_SLOTS = 2;
-constexpr int CHAIN_PAD = 32;  // elements per chain in LAc
+constexpr int CHAIN_PAD = 32;   // elements per chain in LAc
+constexpr int NO_CHAIN = 0x7fff;
 struct Scan {
-    double la0, la1;    // slot s holds element `lane` of the s-th chain inside the window
-    int k0, k1;         // its source state, or -1 if this lane has no element in that slot
-    int thr;            // window threshold (ordinal), warp-uniform
-    unsigned overflow;  // warp-uniform: the column goes through scan_slow()
-    bool dead;          // warp-uniform: no finite estimate in the column
+    double la0, la1;  // slot s holds element `lane` of the s-th chain inside the window (-inf: none)
+    int q0, q1;       // the chains, warp-uniform; NO_CHAIN if the slot is empty
+    float thr;        // window threshold, warp-uniform
+    bool live;        // warp-uniform: the column exists and has a finite estimate
+    bool overflow;    // warp-uniform: the column goes through scan_slow()
 };
 
-__device__ __forceinline__ void scan_fetch(Scan &sc, const float (&cm)[4], const double *__restrict__ LAc, int i, int K,
-                                           int Kp, int lane)
+__device__ __forceinline__ float unford(int o) { return __int_as_float(o >= 0 ? o : (int)((unsigned)(-o) | 0x80000000u)); }
+
+// Straight-line on purpose (no early exits, reductions by redux.sync): the two columns of a warp are scanned
+// back to back and the compiler interleaves them, which halves this latency-bound stretch of the step.
+__device__ __forceinline__ void scan_fetch(Scan &sc, const float (&cm)[4], const double *__restrict__ LAc, int i,
+                                           bool have, int lane)
 {
-    sc.k0 = sc.k1 = -1, sc.la0 = sc.la1 = 0.0, sc.overflow = 0;
-    // the warp's maximum in ONE instruction (redux.sync on the monotone integer image) instead of five shuffle rounds
     const int top = __reduce_max_sync(FULL_MASK, ford(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]))));
-    sc.dead = top <= ford(-FLT_MAX);
-    sc.thr = top - WINDOW_STEPS;
-    if (sc.dead) return;
-    // the four ballots first, then ONE loop over whatever they found: the loop body exists once, which keeps
-    // this latency-bound stretch of the step short in the instruction cache
-    unsigned h0 = __ballot_sync(FULL_MASK, ford(cm[0]) >= sc.thr), h1 = __ballot_sync(FULL_MASK, ford(cm[1]) >= sc.thr);
-    unsigned h2 = __ballot_sync(FULL_MASK, ford(cm[2]) >= sc.thr), h3 = __ballot_sync(FULL_MASK, ford(cm[3]) >= sc.thr);
-    if (LAc == nullptr || __popc(h0) + __popc(h1) + __popc(h2) + __popc(h3) > SCAN_SLOTS) {
-        sc.overflow = 1;
-        return;
-    }
-    const double *col = LAc + (size_t)i * (128 * CHAIN_PAD) + lane;
-    int used = 0;  // warp-uniform count of chains taken
-#pragma unroll 1
-    while (h0 | h1 | h2 | h3) {
-        const int c = h0 ? 0 : h1 ? 1 : h2 ? 2 : 3;
-        const unsigned hc = h0 ? h0 : h1 ? h1 : h2 ? h2 : h3;
-        const int q = 4 * (__ffs(hc) - 1) + c;
-        if (h0) h0 &= h0 - 1;
-        else if (h1) h1 &= h1 - 1;
-        else if (h2) h2 &= h2 - 1;
-        else h3 &= h3 - 1;
-        const int k = q + 128 * lane;  // element `lane` of chain q; the table pads with -inf, so every lane may load
-        // `used` is warp-uniform: branch, so that the load lands in its slot without being consumed
-        if (used == 0) sc.k0 = k, sc.la0 = __ldg(col + q * CHAIN_PAD);
-        else sc.k1 = k, sc.la1 = __ldg(col + q * CHAIN_PAD);
-        ++used;
+    sc.live = have && top > ford(-FLT_MAX);
+    // WINDOW_STEPS float steps below the best estimate, as a float again (clamped at -inf, where every chain is
+    // inside the window and the column goes the slow way): comparing floats equals comparing their integer images
+    sc.thr = unford(max(top - WINDOW_STEPS, ford(-INFINITY)));
+    unsigned m4 = (cm[0] >= sc.thr ? 1u : 0u) | (cm[1] >= sc.thr ? 2u : 0u) | (cm[2] >= sc.thr ? 4u : 0u) |
+                  (cm[3] >= sc.thr ? 8u : 0u);  // this lane's chains inside the window
+    int lq = m4 ? 4 * lane + __ffs(m4) - 1 : NO_CHAIN;
+    sc.q0 = __reduce_min_sync(FULL_MASK, lq);
+    if (lq == sc.q0) m4 &= m4 - 1;
+    lq = m4 ? 4 * lane + __ffs(m4) - 1 : NO_CHAIN;
+    sc.q1 = __reduce_min_sync(FULL_MASK, lq);
+    if (lq == sc.q1) m4 &= m4 - 1;
+    sc.overflow = LAc == nullptr || __any_sync(FULL_MASK, m4 != 0);
+    sc.la0 = sc.la1 = -INFINITY;
+    if (sc.live && !sc.overflow) {
+        // the table pads every chain to CHAIN_PAD elements with -inf, so all lanes load; q0 is a chain whenever
+        // the column is live (the best estimate itself lies inside the window)
+        const double *col = LAc + (size_t)i * (128 * CHAIN_PAD) + lane;
+        sc.la0 = __ldg(col + sc.q0 * CHAIN_PAD);
+        if (sc.q1 != NO_CHAIN) sc.la1 = __ldg(col + sc.q1 * CHAIN_PAD);
     }
 }
 
@@ -399,22 +395,23 @@ __device__ __forceinline__ Best scan_settle(const Scan &sc, const float (&cm)[4]
                                             const double *__restrict__ LAd, int K, int Kp, int i, int lane)
 {
     Best acc{-FLT_MAX, 0x7fffffff};
-    if (!sc.dead) {
+    if (sc.live) {
         if (sc.overflow) {
-            acc = scan_slow(cm[0], cm[1], cm[2], cm[3], sc.thr, tmp, round_base, ncr, rr, sdelta, LAd, K, Kp, i, lane);
+            acc = scan_slow(cm[0], cm[1], cm[2], cm[3], ford(sc.thr), tmp, round_base, ncr, rr, sdelta, LAd, K, Kp, i, lane);
         } else {
-            if (sc.k0 >= 0 && sc.k0 < K) {
-                const float pre = __fadd_rn(tmp, sdelta[sc.k0]);
-                if (ford(__fadd_rn(pre, __double2float_rn(sc.la0))) >= sc.thr) {
+            const int k0 = sc.q0 + 128 * lane, k1 = sc.q1 + 128 * lane;  // element `lane` of either chain
+            if (k0 < K) {
+                const float pre = __fadd_rn(tmp, sdelta[k0]);
+                if (__fadd_rn(pre, __double2float_rn(sc.la0)) >= sc.thr) {
                     const float x = exact_cand(pre, sc.la0);
-                    if (x > -FLT_MAX) best_take(acc, x, sc.k0);
+                    if (x > -FLT_MAX) best_take(acc, x, k0);
                 }
             }
-            if (sc.k1 >= 0 && sc.k1 < K) {
-                const float pre = __fadd_rn(tmp, sdelta[sc.k1]);
-                if (ford(__fadd_rn(pre, __double2float_rn(sc.la1))) >= sc.thr) {
+            if (sc.q1 != NO_CHAIN && k1 < K) {
+                const float pre = __fadd_rn(tmp, sdelta[k1]);
+                if (__fadd_rn(pre, __double2float_rn(sc.la1)) >= sc.thr) {
                     const float x = exact_cand(pre, sc.la1);
-                    if (x > -FLT_MAX) best_take(acc, x, sc.k1);
+                    if (x > -FLT_MAX) best_take(acc, x, k1);
                 }
             }
         }
@@ -682,8 +679,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             if (!have0) continue;  // warp-uniform
             const float *round_base = slab + (size_t)rho * TILE_RW * a.Kp;
             Scan s0, s1;
-            scan_fetch(s0, cm0, a.LAc, i0, a.K, a.Kp, lane);
-            if (have1) scan_fetch(s1, cm1, a.LAc, i1, a.K, a.Kp, lane);
+            scan_fetch(s0, cm0, a.LAc, i0, true, lane);
+            scan_fetch(s1, cm1, a.LAc, i1, have1, lane);
             if (tracing) tr[3] = clock64();
             const Best r0 = scan_settle(s0, cm0, tmp0, round_base, ncr, rr0, sdelta, a.LAd, a.K, a.Kp, i0, lane);
             if (lane == 0) {
