@@ -27,6 +27,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "flashv_internal.h"
 #include "tile_geom.h"
 #include "trellis_common.cuh"
@@ -184,6 +186,11 @@ struct PersistArgs {
     const float *hiC;  // CTA-tiled (float)log A of the columns [col_begin, col_begin+ncol), tile_geom.h
     int col_begin, ncol;  // destination columns this GPU owns (all of them unless the pass is state-sharded)
     const double *LAc;  // chain-major double table of models up to 4096 states (tables.cu), else null
+    // the half-precision filter (k_flash_persist16): models up to 4096 states, unsharded passes
+    const __half *hi16;   // (half)log A, CTA-tiled [cta][iteration of 256 states][column][256], -inf padding
+    const double *LAc16;  // log A chain-major for 256 chains of 16: [(i * 256 + (k & 255)) * 16 + (k >> 8)]
+    int Kp16;             // K rounded up to 256
+    int tm_iters;         // sweep iterations (of 256 states) whose table operands live in tensor memory
     const double *LAd;
     const float *LBf;
     int K, Kp;
@@ -734,6 +741,394 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
     }
 }
 
+
+// =================================================================================================
+// The same pass with a HALF-PRECISION filter (models up to 4096 states, unsharded).
+//
+// The float sweep above moves 4 bytes and issues 3 FP32 instructions per (source, destination) pair only to
+// find out which few sources need the exact evaluation.  A much coarser estimate does that job as well, as
+// long as its error is bounded rigorously and the window is widened to match:
+//     a_k   = delta[k] - c            c = the largest delta of the step (every CTA computes it while staging)
+//     est_k = fl16( fl16(max(a_k, -60000)) + fl16(log A[k][i]) )          one HADD2 per two pairs
+// and the column keeps, per lane, the maxima of 8 chains (chain q = k & 255) with one HMNMX2 per two pairs:
+// 1 instruction and 2 bytes per pair instead of 3 and 4, and no emission term at all (it is common to the
+// column).  Error: with v_k = a_k + log A[k][i] (reals, both terms <= 0, no cancellation) the three half
+// roundings give |est_k - v_k| <= 2.01 * 2^-11 |v_k| + 2^-22 while nothing is clamped, and the reference's
+// candidate differs from tmp + c + v_k by at most 2 float spacings at that magnitude.  So with kt the argmax
+// of est and k* the reference's winner (or any source tying with it):
+//     est(k*) >= est(kt) - W,   W = 2.1 * 2^-10 |est(kt)| + 2^-20 + 2^-20 (|tmp| + |c| + |est(kt)|)
+// (constants rounded up; tests/test_host_logic.py checks the bound on random and adversarial data).  Every
+// chain whose maximum reaches est(kt) - W — 1.24 chains per column on the headline model, 8 or fewer in all
+// but one column in a million — is then evaluated EXACTLY, all 16 elements, from the chain-major double
+// table; the winner is the exact maximum with the lowest index, as the reference's strict '>' finds it.
+// The clamp keeps est finite unless log A is -inf (so a column whose best estimate is -inf is dead for
+// certain); it voids the bound only when est(kt) < -30000, and such a column (never seen) is evaluated in full.
+constexpr int H_PAIRS = 4;  // pairs of chains the fast scan holds (lanes 0-15 one chain, 16-31 the other)
+constexpr float H_CLAMP = -60000.f, H_TRUST = -30000.f;
+
+__device__ __forceinline__ __half2 u2h(uint32_t w) { return *reinterpret_cast<const __half2 *>(&w); }
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<const uint32_t *>(&h); }
+
+__device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st4_raw(uint32_t taddr, const uint4 &v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// Stage delta_{s-1}: poll as delta_wait_load() does, keep the floats for the exact evaluation, find the
+// CTA-wide maximum c on the way (one redux.sync per warp, 14 words through shared memory), and stage
+// fl16(max(delta - c, H_CLAMP)) for the sweep.  Returns c; a value <= -FLT_MAX means no state is alive.
+__device__ __forceinline__ float delta_stage16(const PersistArgs &a, int s, float *sdelta, __half *sdelta16, int *wmax, int ctid)
+{
+    constexpr int NB = 5;  // pairs per thread: 4096 / 2 / NCONS rounded up
+    static_assert(NB * NCONS * 2 >= 4096, "one trip must cover the vector");
+    const int Kp2 = a.Kp >> 1, Kh2 = a.Kp16 >> 1;
+    float2 v[NB];
+    if (s == 1) {
+        const float2 *in2 = reinterpret_cast<const float2 *>(a.d_init);
+#pragma unroll
+        for (int e = 0; e < NB; ++e) {
+            const int t = ctid + e * NCONS;
+            v[e] = t < Kp2 ? __ldcg(in2 + t) : make_float2(0.f, 0.f);
+        }
+    } else {
+        const unsigned long long *x = a.xch + (size_t)((s - 1) & 1) * a.Kp;
+        const unsigned want = step_tag(a, s - 1);
+        unsigned long long w0[NB], w1[NB];
+        unsigned pending = 0;
+#pragma unroll
+        for (int e = 0; e < NB; ++e) {
+            const int t = ctid + e * NCONS;
+            w0[e] = w1[e] = 0;
+            if (t < Kp2 && 2 * t < a.K) pending |= 1u << e;
+        }
+        unsigned long long tw = 0;
+        for (uint32_t spins = 0; pending; ++spins) {
+#pragma unroll
+            for (int e = 0; e < NB; ++e)
+                if (pending >> e & 1u) ld_volatile_2x64(x + 2 * (ctid + e * NCONS), w0[e], w1[e]);
+#pragma unroll
+            for (int e = 0; e < NB; ++e)
+                if (pending >> e & 1u) {
+                    const int k = 2 * (ctid + e * NCONS);
+                    if ((unsigned)(w0[e] >> 32) == want && (k + 1 >= a.K || (unsigned)(w1[e] >> 32) == want)) pending &= ~(1u << e);
+                }
+            if (pending) watchdog(spins * 64u + 63u, tw, a.watchdog_ns);
+        }
+#pragma unroll
+        for (int e = 0; e < NB; ++e) v[e] = make_float2(__uint_as_float((unsigned)w0[e]), __uint_as_float((unsigned)w1[e]));
+    }
+    float mx = -INFINITY;
+    float2 *sd2 = reinterpret_cast<float2 *>(sdelta);
+#pragma unroll
+    for (int e = 0; e < NB; ++e) {
+        const int t = ctid + e * NCONS, k = 2 * t;
+        if (k >= a.K) v[e].x = 0.f;  // padding stays finite (the tables pad with -inf)
+        else mx = fmaxf(mx, v[e].x);
+        if (k + 1 >= a.K) v[e].y = 0.f;
+        else mx = fmaxf(mx, v[e].y);
+        if (t < Kp2) sd2[t] = v[e];
+    }
+    const int wm = __reduce_max_sync(FULL_MASK, ford(mx));
+    if ((ctid & 31) == 0) wmax[ctid >> 5] = wm;
+    named_bar_sync(1, NCONS);
+    const int lane = ctid & 31;
+    const float c = unford(__reduce_max_sync(FULL_MASK, lane < NCW ? wmax[lane] : ford(-INFINITY)));
+    if (c > -FLT_MAX) {
+        __half2 *sh2 = reinterpret_cast<__half2 *>(sdelta16);
+#pragma unroll
+        for (int e = 0; e < NB; ++e) {
+            const int t = ctid + e * NCONS, k = 2 * t;
+            if (t < Kh2) {
+                const float lo = k < a.K ? fmaxf(__fsub_rn(v[e].x, c), H_CLAMP) : 0.f;
+                const float hi = k + 1 < a.K ? fmaxf(__fsub_rn(v[e].y, c), H_CLAMP) : 0.f;
+                sh2[t] = __floats2half2_rn(lo, hi);
+            }
+        }
+    }
+    named_bar_sync(1, NCONS);
+    return c;
+}
+
+struct Scan16 {
+    double la[H_PAIRS];  // pair p: lanes 0-15 hold the elements of chain qa[p], lanes 16-31 those of qb[p]
+    int qa[H_PAIRS], qb[H_PAIRS];  // warp-uniform; NO_CHAIN = empty
+    uint32_t thr2;       // the window threshold, twice, as half2 bits
+    bool live, overflow;  // warp-uniform
+};
+
+// Chains inside the window and their doubles, one column; straight-line like scan_fetch() above.
+__device__ __forceinline__ void scan16_fetch(Scan16 &sc, const __half2 (&m)[4], float tmp, float c, const double *__restrict__ LAc16,
+                                             int i, bool have, int lane)
+{
+    const __half2 mm = __hmax2(__hmax2(m[0], m[1]), __hmax2(m[2], m[3]));
+    const float top = unford(__reduce_max_sync(FULL_MASK, ford(fmaxf(__low2float(mm), __high2float(mm)))));
+    sc.live = have && top > -INFINITY;  // all estimates -inf: no source has an edge into this state
+    const float atop = fabsf(top);
+    const float W = 2.1f * 0x1p-10f * atop + 0x1p-20f + 0x1p-20f * (fabsf(tmp) + fabsf(c) + atop);
+    // below H_TRUST the clamp may have distorted the estimates: everything is inside the window then
+    const __half thr = top >= H_TRUST ? __float2half_rd(top - W) : __float2half_rd(-INFINITY);
+    const __half2 thr2 = __half2half2(thr);
+    sc.thr2 = h2u(thr2);
+    unsigned m8 = 0;  // this lane's chains inside the window: bit 2w + h <-> chain 8 * lane + 2w + h
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const unsigned ge = __hge2_mask(m[w], thr2);
+        m8 |= ((ge & 1u) | ((ge >> 15) & 2u)) << (2 * w);
+    }
+#pragma unroll
+    for (int p = 0; p < H_PAIRS; ++p) sc.la[p] = -INFINITY, sc.qa[p] = sc.qb[p] = NO_CHAIN;
+    const double *col = LAc16 + (size_t)i * 4096 + (lane & 15);
+    int lq = m8 ? 8 * lane + __ffs(m8) - 1 : NO_CHAIN;
+#pragma unroll
+    for (int p = 0; p < H_PAIRS; ++p) {
+        const int qa = __reduce_min_sync(FULL_MASK, lq);
+        if (lq == qa) m8 &= m8 - 1;
+        lq = m8 ? 8 * lane + __ffs(m8) - 1 : NO_CHAIN;
+        const int qb = __reduce_min_sync(FULL_MASK, lq);
+        if (lq == qb) m8 &= m8 - 1;
+        lq = m8 ? 8 * lane + __ffs(m8) - 1 : NO_CHAIN;
+        if (!sc.live || qa == NO_CHAIN) break;  // warp-uniform
+        sc.qa[p] = qa, sc.qb[p] = qb;
+        const int q = lane < 16 ? qa : qb;
+        if (q != NO_CHAIN) sc.la[p] = __ldg(col + q * 16);
+        if (qb == NO_CHAIN) break;
+    }
+    sc.overflow = __any_sync(FULL_MASK, m8 != 0);
+}
+
+// More chains inside the window than the fast scan holds: all of them, two per trip, synchronously.
+__device__ __noinline__ Best scan16_slow(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t thr2, float tmp,
+                                         const float *sdelta, const double *__restrict__ LAc16, int K, int i, int lane)
+{
+    Best acc{-FLT_MAX, 0x7fffffff};
+    const uint32_t mw[4] = {m0, m1, m2, m3};
+    const double *col = LAc16 + (size_t)i * 4096 + (lane & 15);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const unsigned ge = __hge2_mask(u2h(mw[w]), u2h(thr2));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            unsigned hit = __ballot_sync(FULL_MASK, (ge >> (16 * h)) & 1u);
+            while (hit) {
+                const int la_ = __ffs(hit) - 1;
+                hit &= hit - 1;
+                int lb_ = -1;
+                if (hit) lb_ = __ffs(hit) - 1, hit &= hit - 1;
+                const int src = lane < 16 ? la_ : lb_;
+                if (src >= 0) {
+                    const int q = 8 * src + 2 * w + h, k = q + 256 * (lane & 15);
+                    if (k < K) {
+                        const float x = exact_cand(__fadd_rn(tmp, sdelta[k]), __ldg(col + q * 16));
+                        if (x > -FLT_MAX) best_take(acc, x, k);
+                    }
+                }
+            }
+        }
+    }
+    return acc;
+}
+
+__device__ __forceinline__ Best scan16_settle(const Scan16 &sc, const __half2 (&m)[4], float tmp, const float *sdelta,
+                                              const double *__restrict__ LAc16, int K, int i, int lane)
+{
+    Best acc{-FLT_MAX, 0x7fffffff};
+    if (sc.live) {
+        if (sc.overflow) {
+            acc = scan16_slow(h2u(m[0]), h2u(m[1]), h2u(m[2]), h2u(m[3]), sc.thr2, tmp, sdelta, LAc16, K, i, lane);
+        } else {
+#pragma unroll
+            for (int p = 0; p < H_PAIRS; ++p) {
+                if (sc.qa[p] == NO_CHAIN) break;  // warp-uniform
+                const int q = lane < 16 ? sc.qa[p] : sc.qb[p];
+                const int k = q + 256 * (lane & 15);  // every element of a chain inside the window is evaluated exactly
+                if (q != NO_CHAIN && k < K) {
+                    const float x = exact_cand(__fadd_rn(tmp, sdelta[k]), sc.la[p]);
+                    if (x > -FLT_MAX) best_take(acc, x, k);
+                }
+            }
+        }
+    }
+    const int ox = ford(acc.x);
+    const int mo = __reduce_max_sync(FULL_MASK, ox);
+    Best b;
+    b.k = __reduce_min_sync(FULL_MASK, ox == mo ? acc.k : 0x7fffffff);
+    b.x = unford(mo);  // a -0 would come back as +0; it cannot occur (see scan_settle)
+    if (!(b.x > -FLT_MAX)) b.x = -FLT_MAX, b.k = -1;
+    return b;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist16(const PersistArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    int *wmax = reinterpret_cast<int *>(full + MAX_STAGES);  // per-warp maxima of the staged vector
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(full + 2 * MAX_STAGES);
+    float *sdelta = reinterpret_cast<float *>(smem_raw + CTRL_BYTES);
+    __half *sdelta16 = reinterpret_cast<__half *>(sdelta + a.Kp);
+    const uint4 *ring = reinterpret_cast<const uint4 *>(sdelta16 + a.Kp16);  // the table rows that are not in tensor memory
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, b = blockIdx.x;
+    const int c0 = tile_c0(a.ncol, G, b), ncols = tile_c0(a.ncol, G, b + 1) - c0;  // at most TILE_RW
+    const int n_it = a.Kp16 >> 8;               // sweep iterations of 256 source states
+    const int it_tm = min(a.tm_iters, n_it) & ~3;  // those served from tensor memory, four per tcgen05.ld
+    const __half *slab = a.hi16 + (size_t)c0 * a.Kp16;  // [iteration][column][256]
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot);
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+    const uint32_t tbase = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + 128u * (uint32_t)(warp >> 2);
+
+    if (warp == NCW) {
+        // the rows that stay in shared memory: loaded once, one bulk copy per iteration
+        if (lane == 0 && it_tm < n_it && ncols > 0) {
+            const uint32_t per_it = (uint32_t)ncols * 512u;
+            mbar_expect_tx(&full[0], per_it * (uint32_t)(n_it - it_tm));
+            for (int it = it_tm; it < n_it; ++it)
+                bulk_g2s(reinterpret_cast<unsigned char *>(const_cast<uint4 *>(ring)) + (size_t)(it - it_tm) * per_it,
+                         slab + (size_t)it * ncols * 256, per_it, &full[0], 0, false);
+        }
+        return;
+    }
+
+    const int rr0 = warp * CPW, rr1 = rr0 + 1;
+    const bool have0 = rr0 < ncols, have1 = rr1 < ncols;
+    const int rs0 = have0 ? rr0 : 0, rs1 = have1 ? rr1 : rs0;  // a duplicate row stands in for a missing one
+    const int i0 = a.col_begin + c0 + rs0, i1 = a.col_begin + c0 + rs1;
+    if (have0) {
+        for (int it = 0; it < it_tm; ++it) {
+            tmem_st4_raw(tbase + 8u * (uint32_t)it, __ldg(reinterpret_cast<const uint4 *>(slab + ((size_t)it * ncols + rs0) * 256) + lane));
+            tmem_st4_raw(tbase + 8u * (uint32_t)it + 4u, __ldg(reinterpret_cast<const uint4 *>(slab + ((size_t)it * ncols + rs1) * 256) + lane));
+        }
+    }
+    tmem_wait_st();
+    tmem_fence_before();
+    named_bar_sync(1, NCONS);
+    tmem_fence_after();
+
+    int ob_next = __ldg(a.ob + a.L + 1);
+    for (int s = 1; s <= a.nsteps; ++s) {
+        unsigned long long *xout = a.xch + (size_t)(s & 1) * a.Kp;
+        const bool last_step = s == a.nsteps;
+        const int j = a.L + s;
+        const float *tmp_row = a.LBf + (size_t)ob_next * a.Kp;  // F:167
+        const float tmp0 = __ldg(tmp_row + i0), tmp1 = __ldg(tmp_row + i1);
+        if (!last_step) ob_next = __ldg(a.ob + j + 1);
+        const bool keep = j >= a.mid + 1;  // F:242
+        const bool tracing = a.trace != nullptr && s <= TRACE_STEPS && lane == 0 && (warp == 0 || warp == 1);
+        long long *tr = tracing ? a.trace + ((((size_t)(s - 1) * G + b) * 2 + warp) * TRACE_PTS) : nullptr;
+        if (tracing) tr[0] = clock64();
+        const float c = delta_stage16(a, s, sdelta, sdelta16, wmax, tid);
+        if (tracing) tr[1] = clock64();
+        if (s == 1 && it_tm < n_it) mbar_wait(&full[0], 0);
+
+        Best r0{-FLT_MAX, -1}, r1{-FLT_MAX, -1};
+        if (have0 && c > -FLT_MAX) {  // else: no state alive, every column is dead
+            const __half2 ninf = __float2half2_rn(-INFINITY);
+            __half2 m0[4] = {ninf, ninf, ninf, ninf}, m1[4] = {ninf, ninf, ninf, ninf};
+            const uint4 *d4 = reinterpret_cast<const uint4 *>(sdelta16) + lane;
+#define FV_ACC16(D, H0, H1)                                      \
+    m0[0] = __hmax2(m0[0], __hadd2(u2h((D).x), u2h((H0).x)));     \
+    m0[1] = __hmax2(m0[1], __hadd2(u2h((D).y), u2h((H0).y)));     \
+    m0[2] = __hmax2(m0[2], __hadd2(u2h((D).z), u2h((H0).z)));     \
+    m0[3] = __hmax2(m0[3], __hadd2(u2h((D).w), u2h((H0).w)));     \
+    m1[0] = __hmax2(m1[0], __hadd2(u2h((D).x), u2h((H1).x)));     \
+    m1[1] = __hmax2(m1[1], __hadd2(u2h((D).y), u2h((H1).y)));     \
+    m1[2] = __hmax2(m1[2], __hadd2(u2h((D).z), u2h((H1).z)));     \
+    m1[3] = __hmax2(m1[3], __hadd2(u2h((D).w), u2h((H1).w)));
+            // tensor memory and shared memory are separate read paths: odd warps take the shared-memory rows first
+            const bool ring_first = warp & 1;
+#pragma unroll 1
+            for (int ph = 0; ph < 2; ++ph) {
+                if ((ph == 0) != ring_first) {
+#pragma unroll 1
+                    for (int u = 0; u < it_tm; u += 4) {
+                        uint32_t r[32];
+                        uint4 dd[4];
+                        tmem_ld32_raw(tbase + 8u * (uint32_t)u, r);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) dd[e] = d4[(u + e) * 32];
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint4 ha = make_uint4(r[8 * e], r[8 * e + 1], r[8 * e + 2], r[8 * e + 3]);
+                            const uint4 hb = make_uint4(r[8 * e + 4], r[8 * e + 5], r[8 * e + 6], r[8 * e + 7]);
+                            FV_ACC16(dd[e], ha, hb)
+                        }
+                    }
+                } else {
+                    const uint4 *p0 = ring + (size_t)rs0 * 32 + lane, *p1 = ring + (size_t)rs1 * 32 + lane;
+                    const int step4 = ncols * 32;  // uint4 per iteration
+                    int it = it_tm;
+#pragma unroll 1
+                    for (; it + 4 <= n_it; it += 4) {
+                        uint4 ha[4], hb[4], dd[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            ha[e] = p0[(size_t)(it - it_tm + e) * step4];
+                            hb[e] = p1[(size_t)(it - it_tm + e) * step4];
+                            dd[e] = d4[(it + e) * 32];
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { FV_ACC16(dd[e], ha[e], hb[e]) }
+                    }
+#pragma unroll 1
+                    for (; it < n_it; ++it) {
+                        const uint4 h0 = p0[(size_t)(it - it_tm) * step4], h1 = p1[(size_t)(it - it_tm) * step4], d = d4[it * 32];
+                        FV_ACC16(d, h0, h1)
+                    }
+                }
+                if (tracing && ph == 0) tr[6] = clock64();
+            }
+#undef FV_ACC16
+            if (tracing) tr[2] = clock64();
+            Scan16 s0, s1;
+            scan16_fetch(s0, m0, tmp0, c, a.LAc16, i0, true, lane);
+            scan16_fetch(s1, m1, tmp1, c, a.LAc16, i1, have1, lane);
+            if (tracing) tr[3] = clock64();
+            r0 = scan16_settle(s0, m0, tmp0, sdelta, a.LAc16, a.K, i0, lane);
+            r1 = scan16_settle(s1, m1, tmp1, sdelta, a.LAc16, a.K, i1, lane);
+        } else if (tracing) {
+            tr[6] = tr[2] = tr[3] = clock64();
+        }
+        if (lane == 0 && have0) {
+            publish_delta(xout, i0, r0.x, (int)step_tag(a, s));
+            if (last_step) a.d_final[i0] = r0.x;
+            if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i0, r0.k);
+            if (have1) {
+                publish_delta(xout, i1, r1.x, (int)step_tag(a, s));
+                if (last_step) a.d_final[i1] = r1.x;
+                if (keep) psi_store(a.psi, a.psi16, (size_t)(a.psi_row + (j - a.mid - 1)) * a.K + i1, r1.k);
+            }
+        }
+        if (tracing) tr[4] = clock64();
+        named_bar_sync(1, NCONS);  // the staged vectors are overwritten by the next step's load
+        if (tracing) tr[5] = clock64();
+    }
+    tmem_fence_before();
+    named_bar_sync(1, NCONS);
+    if (warp == 0) tmem_dealloc(*tmem_slot);
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 static size_t persist_smem(int Kp, int nstage)
 {
@@ -785,7 +1180,18 @@ static int launch_persist(flashv_model *m, PersistArgs &a)
         }
     }
     const bool peers = a.npeer > 1;
-    const void *fn = a.pinned  ? (peers ? (const void *)k_flash_persist<true, true, true> : (const void *)k_flash_persist<true, true, false>)
+    // Half-precision filter: whenever the model carries the tables (K <= 4096), the pass is not sharded and the
+    // CTA's slice fits tensor memory + shared memory.  FLASHV_F16=0 keeps the float sweep.
+    bool use_f16 = a.hi16 != nullptr && !peers && cols_max <= TILE_RW && env_int("FLASHV_F16", 1) != 0;
+    if (use_f16) {
+        const int n_it = a.Kp16 >> 8;
+        a.tm_iters = env_int("FLASHV_F16_TM_ITERS", 16);  // all of them: measured 1.31 / 1.27 / 1.23 / 1.18 ms for 4 / 8 / 12 / 16 at K=3965
+        const int it_tm = std::min(a.tm_iters, n_it) & ~3;
+        const size_t need = CTRL_BYTES + (size_t)Kp * 4 + (size_t)a.Kp16 * 2 + (size_t)(n_it - it_tm) * cols_max * 512;
+        if (it_tm > 16 || need > (size_t)ctx->smem_optin) use_f16 = false;
+        else smem = std::max(need, (size_t)CTRL_BYTES + 64);
+    }
+    const void *fn = use_f16 ? (const void *)k_flash_persist16 : a.pinned  ? (peers ? (const void *)k_flash_persist<true, true, true> : (const void *)k_flash_persist<true, true, false>)
                      : use_tmem ? (peers ? (const void *)k_flash_persist<true, false, true> : (const void *)k_flash_persist<true, false, false>)
                                 : (peers ? (const void *)k_flash_persist<false, false, true> : (const void *)k_flash_persist<false, false, false>);
     FV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -851,6 +1257,7 @@ int persistent_pass(flashv_plan *p, const Pass &pass)
             return FLASHV_ERR_ARG;
         }
         a.epoch = p->shard_run % 65535u + 1u;
+        a.hi16 = nullptr, a.LAc16 = nullptr, a.Kp16 = 0;
         a.hiC = p->hiC_shard, a.col_begin = p->shard_c0, a.ncol = p->shard_ncol, a.npeer = p->shard_world;
         a.xch = reinterpret_cast<unsigned long long *>(p->shard_region);
         a.psi = p->shard_region + p->shard_psi_off;
@@ -865,6 +1272,7 @@ int persistent_pass(flashv_plan *p, const Pass &pass)
         a.xch = reinterpret_cast<unsigned long long *>(p->d_delta + (size_t)2 * p->max_vec * m->Kp);
         a.psi = p->d_psi;
         a.hiC = m->hiC, a.col_begin = 0, a.ncol = m->K, a.npeer = 1;
+        a.hi16 = m->hi16, a.LAc16 = m->LAc16, a.Kp16 = m->Kp16;
         a.xch_peer[0] = a.xch, a.psi_peer[0] = a.psi;
         a.watchdog_ns = watchdog_limit_ns(false);
     }
@@ -953,6 +1361,7 @@ int persistent_single_step(flashv_model *m, const float *d_in_dev, int o, float 
     FV_CUDA(cudaStreamSynchronize(ctx->stream));
     PersistArgs a;
     a.hiC = m->hiC, a.col_begin = 0, a.ncol = m->K, a.npeer = 1;
+    a.hi16 = m->hi16, a.LAc16 = m->LAc16, a.Kp16 = m->Kp16;
     a.LAd = m->LAd, a.LAc = m->LAc, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.ob = dob, a.L = 0, a.nsteps = 1, a.mid = 0, a.psi_row = 0;
     static unsigned hook_epoch = 0;

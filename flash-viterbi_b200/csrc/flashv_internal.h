@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "flashv.h"
 
 namespace flashv {
@@ -93,6 +95,9 @@ struct flashv_model {
     float *hiT = nullptr;     // [K][Kp]  (float)log A, destination-major: hiT[i][k] = log A[k][i]; pad = -inf
     float *hiC = nullptr;     // K*Kp     the same, CTA-tiled for the persistent engine (tile_geom.h)
     double *LAc = nullptr;    // K*4096   log A chain-major for the persistent engine's window scan (K <= 4096 only)
+    __half *hi16 = nullptr;   // K*Kp16   (half)log A, CTA-tiled for the half-precision filter (K <= 4096 only)
+    double *LAc16 = nullptr;  // K*4096   log A chain-major for that filter: 256 chains of 16
+    int Kp16 = 0;             // K rounded up to 256
     int *csc_ptr = nullptr;       // in-edge lists of the transition graph (flash_sparse.cu); null when the table is dense or K >= 65536
     uint16_t *csc_k = nullptr;
     double *csc_la = nullptr;

@@ -83,6 +83,23 @@ __global__ void k_build_chains(const double *__restrict__ LAd, double *__restric
     LAc[((size_t)i * 128 + (k & 127)) * 32 + (k >> 7)] = k < K ? LAd[(size_t)k * K + i] : -INFINITY;
 }
 
+// The tables of the half-precision filter (k_flash_persist16, flash_persistent.cu), models up to 4096 states:
+// hi16 = (half)log A, rounded from the double directly, tiled [cta][iteration of 256 states][column][256] with
+// the column partition of tile_geom.h and -inf beyond K; LAc16 = log A chain-major for 256 chains of 16.
+__global__ void k_build_tiled16(const double *__restrict__ LAd, __half *__restrict__ hi16, double *__restrict__ LAc16, int K,
+                                int Kp16, int G)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // coalesced reads along i, scattered writes
+    const int k = blockIdx.y;                             // 0 .. 4095
+    if (i >= K) return;
+    const double la = k < K ? LAd[(size_t)k * K + i] : -INFINITY;
+    LAc16[((size_t)i * 256 + (k & 255)) * 16 + (k >> 8)] = la;
+    if (k < Kp16) {
+        const int b = tile_owner(K, G, i), c0 = tile_c0(K, G, b), ncols = tile_c0(K, G, b + 1) - c0;
+        hi16[(size_t)c0 * Kp16 + ((size_t)(k >> 8) * ncols + (i - c0)) * 256 + (k & 255)] = __double2half(la);
+    }
+}
+
 void build_tiled_slice(const double *LAd, float *hiC, int K, int Kp, int col_begin, int ncol, int G, cudaStream_t st)
 {
     k_build_tiled<<<dim3((ncol + 255) / 256, Kp), 256, 0, st>>>(LAd, hiC, K, Kp, col_begin, ncol, G);
@@ -255,6 +272,12 @@ int tables_layouts(flashv_model *m)
         FV_CUDA(cudaMalloc(&m->LAc, (size_t)K * 4096 * sizeof(double)));
         m->bytes += (size_t)K * 4096 * sizeof(double);
         k_build_chains<<<dim3((K + 255) / 256, 4096), 256, 0, ctx->stream>>>(m->LAd, m->LAc, K);
+        FV_CUDA(cudaGetLastError());
+        m->Kp16 = (K + 255) / 256 * 256;
+        FV_CUDA(cudaMalloc(&m->LAc16, (size_t)K * 4096 * sizeof(double)));
+        FV_CUDA(cudaMalloc(&m->hi16, (size_t)K * m->Kp16 * sizeof(__half)));
+        m->bytes += (size_t)K * 4096 * sizeof(double) + (size_t)K * m->Kp16 * sizeof(__half);
+        k_build_tiled16<<<dim3((K + 255) / 256, 4096), 256, 0, ctx->stream>>>(m->LAd, m->hi16, m->LAc16, K, m->Kp16, m->tile_G);
         FV_CUDA(cudaGetLastError());
     }
     if (prep_trace()) {
