@@ -590,6 +590,52 @@ def test_level_kernel_and_step_launches_agree(fv, oracle_mod, golden_models, mon
     ctx.close()
 
 
+@pytest.mark.parametrize("K", [700, 2300, 3965])
+def test_half_filter_regimes(fv, oracle_mod, gpu_ctx, K):
+    """The corners of the half-precision filter of the persistent engine (k_flash_persist16): more chains inside
+    the window than the fast scan holds (many exact ties: the lowest index must win), sources whose delta lies
+    tens of thousands below the best one (clamped estimates, the distrust regime), no state alive at all, and
+    vectors holding -inf — single steps against the oracle, bit for bit."""
+    rng = np.random.RandomState(K)
+    M = 4
+    A = rng.uniform(0.01, 1, (K, K)) * (rng.uniform(0, 1, (K, K)) < 0.3)
+    A[:, 5] = 0.0                      # a state nobody reaches
+    A[:, 7] = 0.0
+    A[::3, 7] = 0.25                   # hundreds of equal edges into state 7 ...
+    A = A / np.maximum(A.sum(axis=1, keepdims=True), 1e-9)
+    A[::3, 7] = A[0, 7]                # ... made bit-identical after the normalisation
+    A = A.astype(np.float32)
+    B = rng.uniform(0.1, 1, (K, M))
+    B = (B / B.sum(axis=1, keepdims=True)).astype(np.float32)
+    Pi = np.full(K, 1.0 / K, np.float32)
+    om = oracle_mod.OracleModel(A, B, Pi)
+    model = fv.Model(gpu_ctx, A, B, Pi)
+
+    def check(d, o, what):
+        want_d, want_psi = om.step(d, o)
+        got_d, got_psi = model.trellis_step(d, o, fv.ENGINE_PERSISTENT)
+        assert np.array_equal(got_psi, want_psi), (what, np.nonzero(got_psi != want_psi)[0][:5])
+        assert np.array_equal(_bits(got_d), _bits(want_d)), what
+        return want_d, want_psi
+
+    flat = np.full(K, np.float32(-17.25), np.float32)
+    d1, psi1 = check(flat, 0, "equal deltas: every third source ties into state 7")
+    assert psi1[7] == 0 and psi1[5] == -1
+    d = (-rng.uniform(0, 5, K)).astype(np.float32)
+    far = rng.uniform(0, 1, K) < 0.98
+    d[far] -= np.float32(rng.choice([3.0e4, 6.5e4, 2.0e5]))
+    check(d, 1, "nearly every source far below the best one")
+    d[~far] = NEG_MAX
+    check(d, 2, "the near sources dead: all estimates clamped")
+    check(np.full(K, NEG_MAX, np.float32), 3, "no state alive")
+    d = d1.copy()
+    d[rng.randint(0, K, K // 2)] = -np.inf
+    check(d, 1, "-inf entries")
+    d2, _ = check((d1 * np.float32(900.0)).astype(np.float32), 2, "large magnitudes")
+    check(d2, 3, "a second step from there")
+    model.close()
+
+
 def test_more_vector_groups_than_grid_y(fv, oracle_mod, gpu_ctx):
     """A deep tree level of a large batch on the per-step engine: 2050 sequences x 256 tasks = 524,800 vectors,
     65,600 groups of 8 — more than gridDim.y allows (65,535).  The groups sit on gridDim.x."""

@@ -197,6 +197,95 @@ def test_sum_first_filter_bound():
     assert widest >= 2  # the ties did produce multi-candidate windows
 
 
+def _half_filter_threshold(top, tmp, c):
+    """The window of scan16_fetch() (flash_persistent.cu) in numpy: float arithmetic, rounded DOWN to half."""
+    top, tmp, c = np.float32(top), np.float32(tmp), np.float32(c)
+    if not top >= np.float32(-30000.0):
+        return np.float16(-np.inf)
+    atop = np.abs(top)
+    W = np.float32(np.float32(2.1) * np.float32(2.0 ** -10) * atop + np.float32(2.0 ** -20)
+                   + np.float32(2.0 ** -20) * (np.abs(tmp) + np.abs(c) + atop))
+    t32 = np.float32(top - W)
+    t16 = np.float16(t32)
+    if np.float32(t16) > t32:
+        t16 = np.nextafter(t16, np.float16(-np.inf))
+    return t16
+
+
+def test_half_precision_filter_bound():
+    """k_flash_persist16 keeps, per chain q = k & 255, the maximum of
+        est_k = fl16( fl16(max(delta[k] - c, -60000)) + fl16(log A[k][i]) ),   c = max(delta),
+    and evaluates exactly every element of every chain whose maximum reaches top - W.  The reference's
+    first-argmax of (float)((double)(float)(tmp + delta[k]) + logA) — and every source tying with it — must sit
+    in such a chain: across magnitudes, near powers of two, with ties, dead sources, -inf edges, a huge spread
+    of delta (the clamp) and emission terms much larger than the rest."""
+    rng = np.random.RandomState(31)
+    NEG = np.float32(-3.4028234663852886e38)
+    widest, slow = 0, 0
+    for trial in range(1500):
+        K = 700
+        kind = trial % 7
+        tmp = np.float32(-rng.uniform(0.0, 6))
+        base = np.float32(-rng.uniform(0, 10) * float(rng.choice([1, 40, 400, 4000])))
+        d = (np.float32(-rng.uniform(0, 8, K)) + base).astype(np.float32)
+        A = rng.uniform(0.01, 1, K) * (rng.uniform(0, 1, K) < 0.4)
+        A = (A / max(A.sum(), 1e-9)).astype(np.float32)
+        if kind == 1:
+            tmp = np.float32(-rng.uniform(20, 90))
+        if kind == 2:  # normalised sums straddling a power of two
+            pw = np.float32(2.0 ** rng.randint(-2, 9))
+            d = (base - np.float32(rng.uniform(0, 1, K)) * pw).astype(np.float32)
+            d[rng.randint(0, K)] = base
+        if kind == 3:
+            A[rng.randint(0, K, 200)] = A[rng.randint(0, K)]  # repeated values: exact ties
+            d[:] = d[0]
+        if kind == 4:
+            d[rng.randint(0, K, 80)] = NEG  # dead sources
+        if kind == 5:  # every source with an edge lies far below the best one: clamp / distrust regime
+            far = rng.uniform(0, 1, K) < 0.97
+            d = np.where(far, d - np.float32(rng.choice([2.0e4, 4.0e4, 7.0e4, 3.0e5])), d).astype(np.float32)
+            A = np.where(far, A, 0).astype(np.float32)
+        if kind == 6:
+            A = (A * (rng.uniform(0, 1, K) < 0.02)).astype(np.float32)  # nearly no edges
+        with np.errstate(divide="ignore"):
+            la = np.log(A.astype(np.float64))
+        pre = (tmp + d).astype(np.float32)
+        with np.errstate(over="ignore", invalid="ignore"):
+            exact = (pre.astype(np.float64) + la).astype(np.float32)
+        best, arg = NEG, -1
+        for k in range(K):
+            if exact[k] > best:
+                best, arg = exact[k], k
+        c = d.max()
+        if not c > NEG:
+            assert arg == -1
+            continue
+        a16 = np.maximum((d - c).astype(np.float32), np.float32(-60000.0)).astype(np.float16)
+        with np.errstate(over="ignore"):
+            b16 = la.astype(np.float16)  # double -> half, one rounding
+            est = (a16.astype(np.float32) + b16.astype(np.float32)).astype(np.float16)  # == correctly rounded half add
+        assert not np.isnan(est.astype(np.float32)).any()
+        top = est.max()
+        if not top > np.float16(-np.inf):
+            assert arg == -1, "an all -inf estimate column must be dead"
+            continue
+        thr = _half_filter_threshold(top, tmp, c)
+        slow += int(np.isinf(np.float32(thr)))
+        chain_max = np.full(256, -np.inf, np.float16)
+        np.maximum.at(chain_max, np.arange(K) & 255, est)
+        chains = np.nonzero(chain_max >= thr)[0]
+        cand = np.nonzero(np.isin(np.arange(K) & 255, chains))[0]
+        widest = max(widest, len(chains))
+        fb, fa = NEG, -1
+        for k in cand:
+            if exact[k] > fb:
+                fb, fa = exact[k], int(k)
+        assert (fb, fa) == (best, arg), (trial, kind)
+        ties = np.nonzero(exact == best)[0] if arg >= 0 else []
+        assert all((k & 255) in chains for k in ties)
+    assert widest >= 2 and slow >= 1  # multi-chain windows and the distrust regime both occurred
+
+
 def test_header_declares_only_exported_symbols(fv):
     text = (ROOT / "include" / "flashv.h").read_text()
     declared = sorted(set(re.findall(r"\b(flashv_[a-z_A-Z0-9]+)\s*\(", text)))
