@@ -13,6 +13,8 @@
 #include <algorithm>
 
 #include "flashv_internal.h"
+#include "half_filter.cuh"
+#include "tile_geom.h"
 #include "trellis_common.cuh"
 
 namespace flashv {
@@ -543,6 +545,222 @@ static int launch_level(flashv_plan *p, const Pass &pass, LevelArgs &la, bool *d
     return FLASHV_OK;
 }
 
+
+// ---- the same level in ONE launch with the half-precision filter (models up to 4096 states) ------------------
+// k_flash_level spreads (vector group, column tile) items over the CTAs and streams the float table from L2 for
+// every item.  Here the roles are those of the pass kernel k_flash_persist16 (flash_persistent.cu; the filter and
+// its window: DESIGN.md §4): CTA b owns the destination columns [tile_c0(b), tile_c0(b+1)) for the whole launch,
+// its slice of (half)log A is parked in tensor memory once, and every step it walks ALL vectors of the level over
+// those columns, VG vectors per trip: one tcgen05.ld feeds VG vectors (HADD2 + HMNMX2 per two updates), the
+// winners come from the chain-major double table, delta ping-pongs through global memory as plain floats with a
+// grid barrier per step, exactly as in k_flash_level.  Start vectors, last-column steps, end states and the walk
+// back are the shared bodies above.
+constexpr int L16_WARPS = 14, L16_THREADS = L16_WARPS * 32, L16_PAIRS = 2;
+
+template <int VG>
+__global__ void __launch_bounds__(L16_THREADS, 1) k_flash_level16(const LevelArgs la, const __half *__restrict__ hi16,
+                                                                    const double *__restrict__ LAc16, int Kp16)
+{
+    extern __shared__ __align__(16) unsigned char smem16[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ int wmax[VG][L16_WARPS];
+    const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = la.st.K, Kp = la.st.Kp, T = la.st.T;
+    float *sdelta = reinterpret_cast<float *>(smem16);                       // [VG][Kp] floats, for the exact evaluation
+    __half *sdelta16 = reinterpret_cast<__half *>(sdelta + (size_t)VG * Kp);  // [VG][Kp16] fl16(delta - max), for the sweep
+    unsigned long long bar_target = la.bar_base;
+
+    const int c0 = tile_c0(K, G, b), ncols = tile_c0(K, G, b + 1) - c0;  // at most 28: two per warp
+    const int n_it = Kp16 >> 8;
+    const __half *slab = hi16 + (size_t)c0 * Kp16;  // [iteration][column][256]
+    if (warp == 0) tmem_alloc(&tmem_slot);
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+    const uint32_t tbase = tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + 128u * (uint32_t)(warp >> 2);
+    const int rr0 = 2 * warp, rr1 = rr0 + 1;
+    const bool have0 = rr0 < ncols, have1 = rr1 < ncols;
+    const int rs0 = have0 ? rr0 : 0, rs1 = have1 ? rr1 : rs0;  // a duplicate row stands in for a missing one
+    const int i0 = c0 + rs0, i1 = c0 + rs1;
+    if (have0)
+        for (int it = 0; it < n_it; ++it) {
+            tmem_st4_raw(tbase + 8u * (uint32_t)it, __ldg(reinterpret_cast<const uint4 *>(slab + ((size_t)it * ncols + rs0) * 256) + lane));
+            tmem_st4_raw(tbase + 8u * (uint32_t)it + 4u, __ldg(reinterpret_cast<const uint4 *>(slab + ((size_t)it * ncols + rs1) * 256) + lane));
+        }
+    tmem_wait_st();
+    tmem_fence_before();
+
+    for (int v = b; v < la.nvec; v += G)
+        init_vector(la.st.vecs[v], v, la.st.ob, la.ans, T, la.st.LAd, la.LBd, la.LPi, K, Kp, la.d0, tid, L16_THREADS);
+    grid_barrier(la.bar, bar_target += gridDim.x);
+    tmem_fence_after();
+
+    constexpr int NB = 5;  // pairs of delta values per thread and vector: 4096 / 2 / 448 rounded up
+    const int Kp2 = Kp >> 1, Kh2 = Kp16 >> 1;
+    for (int s = 1; s <= la.max_steps; ++s) {
+        const int n_act = la.nactive[s], n_cont = la.full_range ? n_act : la.nactive[s + 1];
+        const float *din = (s & 1) ? la.d0 : la.d1;
+        float *dout = (s & 1) ? la.d1 : la.d0;
+        for (int v0 = 0; v0 < n_cont; v0 += VG) {
+            const int nv = min(VG, n_cont - v0);
+            // ---- stage VG vectors: floats, their maxima, then the half-precision images ----
+            float2 val[VG][NB];
+#pragma unroll
+            for (int q = 0; q < VG; ++q)
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const int t = tid + e * L16_THREADS;
+                    val[q][e] = (q < nv && t < Kp2) ? __ldcg(reinterpret_cast<const float2 *>(din + (size_t)(v0 + q) * Kp) + t)
+                                                    : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+            for (int q = 0; q < VG; ++q) {
+                float mx = -INFINITY;
+                float2 *sd2 = reinterpret_cast<float2 *>(sdelta + (size_t)q * Kp);
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const int t = tid + e * L16_THREADS, k = 2 * t;
+                    if (k >= K) val[q][e].x = 0.f;  // padding stays finite (the table pads with -inf)
+                    else mx = fmaxf(mx, val[q][e].x);
+                    if (k + 1 >= K) val[q][e].y = 0.f;
+                    else mx = fmaxf(mx, val[q][e].y);
+                    if (t < Kp2) sd2[t] = val[q][e];
+                }
+                const int wm = __reduce_max_sync(FULL_MASK, ford(mx));
+                if (lane == 0) wmax[q][warp] = wm;
+            }
+            __syncthreads();
+            float cmax[VG];
+#pragma unroll
+            for (int q = 0; q < VG; ++q) {
+                cmax[q] = unford(__reduce_max_sync(FULL_MASK, lane < L16_WARPS ? wmax[q][lane] : ford(-INFINITY)));
+                __half2 *sh2 = reinterpret_cast<__half2 *>(sdelta16 + (size_t)q * Kp16);
+                const float c = cmax[q] > -FLT_MAX ? cmax[q] : 0.f;  // no state alive: the vector is skipped below
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const int t = tid + e * L16_THREADS, k = 2 * t;
+                    if (t < Kh2) {
+                        const float lo = k < K ? fmaxf(__fsub_rn(val[q][e].x, c), H_CLAMP) : 0.f;
+                        const float hi = k + 1 < K ? fmaxf(__fsub_rn(val[q][e].y, c), H_CLAMP) : 0.f;
+                        sh2[t] = __floats2half2_rn(lo, hi);
+                    }
+                }
+            }
+            __syncthreads();
+
+            if (have0) {
+                // ---- sweep: every tensor-memory load meets VG vectors ----
+                const __half2 ninf = __float2half2_rn(-INFINITY);
+                __half2 m[VG][2][4];
+#pragma unroll
+                for (int q = 0; q < VG; ++q)
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) m[q][0][w] = m[q][1][w] = ninf;
+                const uint4 *d4 = reinterpret_cast<const uint4 *>(sdelta16) + lane;
+                const int q4 = Kp16 >> 3;  // uint4 per staged vector
+#pragma unroll 1
+                for (int u = 0; u < n_it; u += 4) {
+                    uint32_t r[32];
+                    tmem_ld32_raw(tbase + 8u * (uint32_t)u, r);
+                    tmem_wait_ld();
+                    const int ne = min(4, n_it - u);  // the table pads to whole iterations; a short tail reads unused columns
+#pragma unroll
+                    for (int q = 0; q < VG; ++q) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (e < ne) {
+                                const uint4 d = d4[(size_t)q * q4 + (u + e) * 32];
+#pragma unroll
+                                for (int w = 0; w < 4; ++w) {
+                                    const uint32_t dw = w == 0 ? d.x : w == 1 ? d.y : w == 2 ? d.z : d.w;
+                                    m[q][0][w] = __hmax2(m[q][0][w], __hadd2(u2h(dw), u2h(r[8 * e + w])));
+                                    m[q][1][w] = __hmax2(m[q][1][w], __hadd2(u2h(dw), u2h(r[8 * e + 4 + w])));
+                                }
+                            }
+                        }
+                    }
+                }
+                // ---- winners, two vectors (four columns) at a time so that their HBM round trips overlap ----
+#pragma unroll
+                for (int q = 0; q < VG; q += 2) {
+                    Scan16T<L16_PAIRS> sc[2][2];
+                    float tmp[2][2];
+                    bool on[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        on[h] = q + h < nv && cmax[q + h < VG ? q + h : 0] > -FLT_MAX;
+                        const VecDesc &vd = la.st.vecs[v0 + (q + h < nv ? q + h : 0)];
+                        const float *tmp_row = la.st.LBf + (size_t)la.st.ob[(size_t)vd.seq * T + vd.L + s] * Kp;
+                        tmp[h][0] = __ldg(tmp_row + i0), tmp[h][1] = __ldg(tmp_row + i1);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (q + h >= VG) continue;
+                        const float c = cmax[q + h];
+                        scan16_fetch(sc[h][0], m[q + h][0], tmp[h][0], c, LAc16, i0, on[h], lane);
+                        scan16_fetch(sc[h][1], m[q + h][1], tmp[h][1], c, LAc16, i1, on[h] && have1, lane);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (q + h >= VG || q + h >= nv) continue;  // warp-uniform
+                        const int v = v0 + q + h;
+                        const VecDesc &vd = la.st.vecs[v];
+                        const int j = vd.L + s;
+                        const float *sd = sdelta + (size_t)(q + h) * Kp;
+                        const Best r0 = scan16_settle(sc[h][0], m[q + h][0], tmp[h][0], sd, LAc16, K, i0, lane);
+                        const Best r1 = scan16_settle(sc[h][1], m[q + h][1], tmp[h][1], sd, LAc16, K, i1, lane);
+                        if (lane == 0) {
+                            dout[(size_t)v * Kp + i0] = r0.x;
+                            if (j >= vd.mid + 1) psi_store(la.st.psi, la.st.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + i0, r0.k);
+                            if (have1) {
+                                dout[(size_t)v * Kp + i1] = r1.x;
+                                if (j >= vd.mid + 1) psi_store(la.st.psi, la.st.psi16, (size_t)(vd.psi_row + (j - vd.mid - 1)) * K + i1, r1.k);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // the staged vectors are replaced by the next trip's
+        }
+        for (int v = n_cont + b; v < n_act; v += G) last_column_body(la.st, s, din, v, la.ans);
+        grid_barrier(la.bar, bar_target += gridDim.x);
+    }
+    const float *final_delta = (la.max_steps & 1) ? la.d1 : la.d0;
+    for (int v = b; v < la.nvec; v += G) {
+        const VecDesc vd = la.st.vecs[v];
+        end_body(vd, v, final_delta, K, Kp, T, la.ans, la.score, la.endstate);
+        if (tid == 0) backtrack_vector(vd, la.endstate[v], la.st.psi, la.st.psi16, K, T, la.ismid, la.ans);
+        __syncthreads();
+    }
+    tmem_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot);
+}
+
+template <int VG>
+static int launch_level16(flashv_plan *p, const Pass &pass, LevelArgs &la, bool *done)
+{
+    flashv_model *m = p->model;
+    flashv_ctx *ctx = m->ctx;
+    const size_t smem = (size_t)VG * ((size_t)m->Kp * 4 + (size_t)m->Kp16 * 2);
+    const void *fn = (const void *)k_flash_level16<VG>;
+    FV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    FV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, L16_THREADS, smem));
+    const int grid = m->tile_G;  // the grid the half-precision table was tiled for
+    if (per_sm < 1 || grid > ctx->sm_count) return FLASHV_OK;  // does not fit: the caller falls back
+    la.bar = reinterpret_cast<unsigned long long *>(p->d_sync), la.bar_base = p->bar_count;
+    p->bar_count += (unsigned long long)(1 + pass.max_steps) * grid;
+    const __half *hi16 = m->hi16;
+    const double *LAc16 = m->LAc16;
+    int Kp16 = m->Kp16;
+    void *params[] = {(void *)&la, (void *)&hi16, (void *)&LAc16, (void *)&Kp16};
+    FV_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(L16_THREADS), params, smem, ctx->stream));
+    ++p->launches;
+    *done = true;
+    return FLASHV_OK;
+}
+
 // Returns with *done = true when the whole pass (start vectors .. Ans[mid]) ran in one launch.
 static int level_pass(flashv_plan *p, const Pass &pass, bool *done)
 {
@@ -552,7 +770,7 @@ static int level_pass(flashv_plan *p, const Pass &pass, bool *done)
     // Measured (K=3965, T=256, same box): one launch per level against one per step — N=1 9.65 / 10.12 ms, N=8
     // 6.29 / 6.53 ms, N=64 2.77 / 2.75 ms, N=127 2.22 / 2.16 ms.  A level of one or two steps has nothing to
     // amortise the extra grid barriers over, so short levels keep the per-step launches.
-    const int min_steps = getenv("FLASHV_LEVEL_MIN_STEPS") ? atoi(getenv("FLASHV_LEVEL_MIN_STEPS")) : 5;
+    const int min_steps = getenv("FLASHV_LEVEL_MIN_STEPS") ? atoi(getenv("FLASHV_LEVEL_MIN_STEPS")) : (m->hi16 ? 2 : 5);
     if (pass.max_steps < min_steps) return FLASHV_OK;
     LevelArgs la;
     StepArgs &a = la.st;
@@ -564,6 +782,12 @@ static int level_pass(flashv_plan *p, const Pass &pass, bool *done)
     la.nactive = p->d_nactive + pass.nactive_off;
     la.d0 = p->d_delta, la.d1 = p->d_delta + (size_t)p->max_vec * m->Kp;
     la.ans = p->d_ans, la.score = p->d_score, la.endstate = p->d_endstate, la.ismid = p->d_ismid;
+    // models up to 4096 states: the half-precision filter over a tensor-memory-resident table (FLASHV_LEVEL16=0: the float sweep)
+    if (m->hi16 && (!getenv("FLASHV_LEVEL16") || atoi(getenv("FLASHV_LEVEL16")) != 0)) {
+        const int vg = getenv("FLASHV_LEVEL16_VG") ? atoi(getenv("FLASHV_LEVEL16_VG")) : 4;
+        int rc = (vg >= 4 && pass.nvec > 2) ? launch_level16<4>(p, pass, la, done) : launch_level16<2>(p, pass, la, done);
+        if (rc != FLASHV_OK || *done) return rc;
+    }
     const size_t vec_bytes = (size_t)m->Kp * 4;
     if (pass.nvec >= 5 && 8 * vec_bytes <= 200 * 1024) return launch_level<8, 2, 16>(p, pass, la, done);
     if (pass.nvec >= 3 && 4 * vec_bytes <= 200 * 1024) return launch_level<4, 2, 8>(p, pass, la, done);
