@@ -165,6 +165,9 @@ struct PersistArgs {
     const double *LAc16;  // log A chain-major for 256 chains of 16: [(i * 256 + (k & 255)) * 16 + (k >> 8)]
     int Kp16;             // K rounded up to 256
     int tm_iters;         // sweep iterations (of 256 states) whose table operands live in tensor memory
+    const float *LBmax;   // [M] the largest emission term of every symbol
+    int exact_max;        // 1: find the maximum of every staged vector exactly (one more CTA barrier per step) instead of bounding it
+    double lamax;         // the largest log A of the model
     const double *LAd;
     const float *LBf;
     int K, Kp;
@@ -735,10 +738,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
 // table; the winner is the exact maximum with the lowest index, as the reference's strict '>' finds it.
 // The clamp keeps est finite unless log A is -inf (so a column whose best estimate is -inf is dead for
 // certain); it voids the bound only when est(kt) < -30000, and such a column (never seen) is evaluated in full.
-// Stage delta_{s-1}: poll as delta_wait_load() does, keep the floats for the exact evaluation, find the
-// CTA-wide maximum c on the way (one redux.sync per warp, 14 words through shared memory), and stage
-// fl16(max(delta - c, H_CLAMP)) for the sweep.  Returns c; a value <= -FLT_MAX means no state is alive.
-__device__ __forceinline__ float delta_stage16(const PersistArgs &a, int s, float *sdelta, __half *sdelta16, int *wmax, int ctid)
+// Stage delta_{s-1}: poll as delta_wait_load() does, keep the floats for the exact evaluation, and stage
+// fl16(max(delta - c, H_CLAMP)) for the sweep.  c must be >= every entry and close to the largest one.  In the
+// first step it IS the largest one (one redux.sync per warp, 14 words through shared memory, one more CTA
+// barrier); afterwards the caller passes a bound it derived from the previous vector's maximum BEFORE the poll
+// (c_bound), so no barrier separates the poll from the conversion, and this call only leaves the per-warp maxima
+// of the vector it stages in wmax[] for the next step's bound.  Returns c; <= -FLT_MAX means no state is alive.
+__device__ __forceinline__ float delta_stage16(const PersistArgs &a, int s, float *sdelta, __half *sdelta16, int *wmax, float c_bound,
+                                               int ctid)
 {
     constexpr int NB = 5;  // pairs per thread: 4096 / 2 / NCONS rounded up
     static_assert(NB * NCONS * 2 >= 4096, "one trip must cover the vector");
@@ -791,9 +798,12 @@ __device__ __forceinline__ float delta_stage16(const PersistArgs &a, int s, floa
     }
     const int wm = __reduce_max_sync(FULL_MASK, ford(mx));
     if ((ctid & 31) == 0) wmax[ctid >> 5] = wm;
-    named_bar_sync(1, NCONS);
-    const int lane = ctid & 31;
-    const float c = unford(__reduce_max_sync(FULL_MASK, lane < NCW ? wmax[lane] : ford(-INFINITY)));
+    float c = c_bound;
+    if (s == 1 || a.exact_max) {
+        named_bar_sync(1, NCONS);
+        const int lane = ctid & 31;
+        c = unford(__reduce_max_sync(FULL_MASK, lane < NCW ? wmax[lane] : ford(-INFINITY)));
+    }
     if (c > -FLT_MAX) {
         __half2 *sh2 = reinterpret_cast<__half2 *>(sdelta16);
 #pragma unroll
@@ -814,11 +824,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist16(const PersistAr
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
-    int *wmax = reinterpret_cast<int *>(full + MAX_STAGES);  // per-warp maxima of the staged vector
+    int *wmax_base = reinterpret_cast<int *>(full + MAX_STAGES);  // [2][16] per-warp maxima of the staged vectors
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(full + 2 * MAX_STAGES);
-    float *sdelta = reinterpret_cast<float *>(smem_raw + CTRL_BYTES);
-    __half *sdelta16 = reinterpret_cast<__half *>(sdelta + a.Kp);
-    const uint4 *ring = reinterpret_cast<const uint4 *>(sdelta16 + a.Kp16);  // the table rows that are not in tensor memory
+    // (Two copies of the staged vector and no CTA barrier at the end of a step were tried: the warps that finish
+    // early then spin in the next poll and take issue slots from the stragglers, whose scan -> publish chain IS the
+    // critical path of the whole grid — 1.10 -> 1.53 ms.  Parked at a barrier they cost nothing.)
+    const size_t stage_bytes = (size_t)a.Kp * 4 + (size_t)a.Kp16 * 2;
+    unsigned char *stage_base = smem_raw + CTRL_BYTES;
+    const uint4 *ring = reinterpret_cast<const uint4 *>(stage_base + stage_bytes);  // the table rows that are not in tensor memory
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, b = blockIdx.x;
@@ -864,19 +877,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist16(const PersistAr
     named_bar_sync(1, NCONS);
     tmem_fence_after();
 
-    int ob_next = __ldg(a.ob + a.L + 1);
+    int ob_next = __ldg(a.ob + a.L + 1), ob_prev = 0;
     for (int s = 1; s <= a.nsteps; ++s) {
+        float *sdelta = reinterpret_cast<float *>(stage_base);
+        __half *sdelta16 = reinterpret_cast<__half *>(sdelta + a.Kp);
+        int *wmax = wmax_base + 16 * (s & 1);
         unsigned long long *xout = a.xch + (size_t)(s & 1) * a.Kp;
         const bool last_step = s == a.nsteps;
         const int j = a.L + s;
         const float *tmp_row = a.LBf + (size_t)ob_next * a.Kp;  // F:167
         const float tmp0 = __ldg(tmp_row + i0), tmp1 = __ldg(tmp_row + i1);
+        // A bound on the vector about to arrive, from the maximum of the one before it (left in wmax[] by the
+        // previous step's staging): delta_{s-1}[i] = fl32(fl64(fl32(tmp_i + delta_{s-2}[k]) + log A[k][i]))
+        //   <= fl32(fl64(fl32(tmpmax + max delta_{s-2}) + max log A))  — every rounding is monotone.
+        float c_bound = 0.f;
+        if (s > 1) {
+            const float prev = unford(__reduce_max_sync(FULL_MASK, lane < NCW ? wmax_base[16 * ((s - 1) & 1) + lane] : ford(-INFINITY)));
+            c_bound = prev > -FLT_MAX ? exact_cand(__fadd_rn(__ldg(a.LBmax + ob_prev), prev), a.lamax) : -FLT_MAX;
+            if (!(c_bound > -FLT_MAX)) c_bound = -FLT_MAX;
+        }
+        ob_prev = ob_next;
         if (!last_step) ob_next = __ldg(a.ob + j + 1);
         const bool keep = j >= a.mid + 1;  // F:242
         const bool tracing = a.trace != nullptr && s <= TRACE_STEPS && lane == 0 && (warp == 0 || warp == 1);
         long long *tr = tracing ? a.trace + ((((size_t)(s - 1) * G + b) * 2 + warp) * TRACE_PTS) : nullptr;
         if (tracing) tr[0] = clock64();
-        const float c = delta_stage16(a, s, sdelta, sdelta16, wmax, tid);
+        const float c = delta_stage16(a, s, sdelta, sdelta16, wmax, c_bound, tid);
         if (tracing) tr[1] = clock64();
         if (s == 1 && it_tm < n_it) mbar_wait(&full[0], 0);
 
@@ -960,7 +986,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist16(const PersistAr
             }
         }
         if (tracing) tr[4] = clock64();
-        named_bar_sync(1, NCONS);  // the staged vectors are overwritten by the next step's load
+        named_bar_sync(1, NCONS);  // the staged vector is overwritten by the next step's load; finished warps wait here, not in the poll
         if (tracing) tr[5] = clock64();
     }
     tmem_fence_before();
@@ -1024,6 +1050,7 @@ static int launch_persist(flashv_model *m, PersistArgs &a)
     bool use_f16 = a.hi16 != nullptr && !peers && cols_max <= TILE_RW && env_int("FLASHV_F16", 1) != 0;
     if (use_f16) {
         const int n_it = a.Kp16 >> 8;
+        a.exact_max = env_int("FLASHV_F16_EXACT_MAX", 0);
         a.tm_iters = env_int("FLASHV_F16_TM_ITERS", 16);  // all of them: measured 1.31 / 1.27 / 1.23 / 1.18 ms for 4 / 8 / 12 / 16 at K=3965
         const int it_tm = std::min(a.tm_iters, n_it) & ~3;
         const size_t need = CTRL_BYTES + (size_t)Kp * 4 + (size_t)a.Kp16 * 2 + (size_t)(n_it - it_tm) * cols_max * 512;
@@ -1096,7 +1123,7 @@ int persistent_pass(flashv_plan *p, const Pass &pass)
             return FLASHV_ERR_ARG;
         }
         a.epoch = p->shard_run % 65535u + 1u;
-        a.hi16 = nullptr, a.LAc16 = nullptr, a.Kp16 = 0;
+        a.hi16 = nullptr, a.LAc16 = nullptr, a.Kp16 = 0, a.LBmax = nullptr, a.lamax = 0.0;
         a.hiC = p->hiC_shard, a.col_begin = p->shard_c0, a.ncol = p->shard_ncol, a.npeer = p->shard_world;
         a.xch = reinterpret_cast<unsigned long long *>(p->shard_region);
         a.psi = p->shard_region + p->shard_psi_off;
@@ -1111,7 +1138,7 @@ int persistent_pass(flashv_plan *p, const Pass &pass)
         a.xch = reinterpret_cast<unsigned long long *>(p->d_delta + (size_t)2 * p->max_vec * m->Kp);
         a.psi = p->d_psi;
         a.hiC = m->hiC, a.col_begin = 0, a.ncol = m->K, a.npeer = 1;
-        a.hi16 = m->hi16, a.LAc16 = m->LAc16, a.Kp16 = m->Kp16;
+        a.hi16 = m->hi16, a.LAc16 = m->LAc16, a.Kp16 = m->Kp16, a.LBmax = m->LBmax, a.lamax = m->lamax;
         a.xch_peer[0] = a.xch, a.psi_peer[0] = a.psi;
         a.watchdog_ns = watchdog_limit_ns(false);
     }
@@ -1200,7 +1227,7 @@ int persistent_single_step(flashv_model *m, const float *d_in_dev, int o, float 
     FV_CUDA(cudaStreamSynchronize(ctx->stream));
     PersistArgs a;
     a.hiC = m->hiC, a.col_begin = 0, a.ncol = m->K, a.npeer = 1;
-    a.hi16 = m->hi16, a.LAc16 = m->LAc16, a.Kp16 = m->Kp16;
+    a.hi16 = m->hi16, a.LAc16 = m->LAc16, a.Kp16 = m->Kp16, a.LBmax = m->LBmax, a.lamax = m->lamax;
     a.LAd = m->LAd, a.LAc = m->LAc, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.ob = dob, a.L = 0, a.nsteps = 1, a.mid = 0, a.psi_row = 0;
     static unsigned hook_epoch = 0;

@@ -98,6 +98,8 @@ struct flashv_model {
     __half *hi16 = nullptr;   // K*Kp16   (half)log A, CTA-tiled for the half-precision filter (K <= 4096 only)
     double *LAc16 = nullptr;  // K*4096   log A chain-major for that filter: 256 chains of 16
     int Kp16 = 0;             // K rounded up to 256
+    float *LBmax = nullptr;   // M         the largest emission term of every symbol
+    double lamax = 0.0;       //           the largest log A (host copy)
     int *csc_ptr = nullptr;       // in-edge lists of the transition graph (flash_sparse.cu); null when the table is dense or K >= 65536
     uint16_t *csc_k = nullptr;
     double *csc_la = nullptr;

@@ -26,6 +26,8 @@
 #include <thread>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 #include "flashv_internal.h"
 #include "tile_geom.h"
 
@@ -130,6 +132,7 @@ int tables_alloc(flashv_model *m)
     const size_t nA = (size_t)K * K;
     FV_CUDA(cudaMalloc(&m->LAd, nA * sizeof(double)));
     FV_CUDA(cudaMalloc(&m->LBf, (size_t)M * Kp * sizeof(float)));
+    FV_CUDA(cudaMalloc(&m->LBmax, (size_t)M * sizeof(float)));
     FV_CUDA(cudaMalloc(&m->LBd, (size_t)M * K * sizeof(double)));
     FV_CUDA(cudaMalloc(&m->LPi, (size_t)K * sizeof(double)));
     FV_CUDA(cudaMalloc(&m->scratch_f, (size_t)4 * Kp * sizeof(float)));
@@ -226,16 +229,18 @@ int tables_logs(flashv_model *m, const float *A, const float *B, const float *Pi
 
     if (prep_trace()) fprintf(stderr, "[flashv prep] log A rows [%d,%d) issued: %.2f ms\n", row_lo, row_hi, ms_since(t0));
     std::vector<double> hLB((size_t)M * K), hLPi((size_t)K);
-    std::vector<float> hLBf((size_t)M * Kp, 0.0f);
+    std::vector<float> hLBf((size_t)M * Kp, 0.0f), hLBmax((size_t)M, -INFINITY);
     for (int i = 0; i < K; ++i) {
         for (int o = 0; o < M; ++o) {
             double v = log((double)B[(size_t)i * M + o]);  // F:142 / F:167
             hLB[(size_t)o * K + i] = v;
             hLBf[(size_t)o * Kp + i] = (float)v;  // "tmp = log(...)" stored into a float, F:167
+            hLBmax[o] = fmaxf(hLBmax[o], (float)v);  // the largest emission term of symbol o (k_flash_persist16's bound on max delta)
         }
         hLPi[i] = log((double)Pi[i]);  // F:142
     }
     FV_CUDA(cudaMemcpyAsync(m->LBf, hLBf.data(), hLBf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    FV_CUDA(cudaMemcpyAsync(m->LBmax, hLBmax.data(), hLBmax.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     FV_CUDA(cudaMemcpyAsync(m->LBd, hLB.data(), hLB.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     FV_CUDA(cudaMemcpyAsync(m->LPi, hLPi.data(), hLPi.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     FV_CUDA(cudaStreamSynchronize(ctx->stream));  // the vectors are on this frame; the staging buffers are reusable
@@ -279,6 +284,17 @@ int tables_layouts(flashv_model *m)
         m->bytes += (size_t)K * 4096 * sizeof(double) + (size_t)K * m->Kp16 * sizeof(__half);
         k_build_tiled16<<<dim3((K + 255) / 256, 4096), 256, 0, ctx->stream>>>(m->LAd, m->hi16, m->LAc16, K, m->Kp16, m->tile_G);
         FV_CUDA(cudaGetLastError());
+        // the largest log A of the model: with the largest emission term it bounds a step's best delta from the previous one
+        double *d_res = nullptr;
+        void *tmp_store = nullptr;
+        size_t tmp_bytes = 0;
+        FV_CUDA(cub::DeviceReduce::Max(tmp_store, tmp_bytes, m->LAd, d_res, (size_t)K * K, ctx->stream));  // size query
+        FV_CUDA(cudaMalloc(&tmp_store, tmp_bytes));
+        FV_CUDA(cudaMalloc(&d_res, sizeof(double)));
+        FV_CUDA(cub::DeviceReduce::Max(tmp_store, tmp_bytes, m->LAd, d_res, (size_t)K * K, ctx->stream));
+        FV_CUDA(cudaMemcpyAsync(&m->lamax, d_res, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        FV_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp_store), cudaFree(d_res);
     }
     if (prep_trace()) {
         cudaStreamSynchronize(ctx->stream);
