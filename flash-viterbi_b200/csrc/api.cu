@@ -394,6 +394,15 @@ extern "C" int flashv_plan_create(flashv_model *m, int T, int N, int batch, int 
     PL_ALLOC(p->d_ismid, (size_t)T);
     PL_ALLOC(p->d_endstate, (size_t)p->max_vec * 4);
     PL_ALLOC(p->d_sync, 256);
+    {
+        // scratch of the parallel walk back (k_flash_backtrack_par): one composed map of K states per window of rows
+        const size_t row_bytes = (size_t)K * (p->psi16 ? 2 : 4);
+        const int win_rows = (int)((200 * 1024 - 32) / row_bytes);
+        if (B == 0 && batch == 1 && win_rows >= 4) {
+            p->bt_windows = (T + win_rows - 1) / win_rows + 1;
+            PL_ALLOC(p->d_btmap, (size_t)p->bt_windows * ((size_t)K + 1) * 4);
+        }
+    }
     if (B == 0) {
         PL_ALLOC(p->d_delta, delta_bytes);
     } else {
@@ -430,7 +439,7 @@ extern "C" void flashv_plan_destroy(flashv_plan *p)
         if (p->peer_ipc[r]) cudaIpcCloseMemHandle(p->peer_region[r]);
     cudaFree(p->hiC_shard), cudaFree(p->shard_region), cudaFree(p->d_lvl_mid);
     cudaFree(p->d_ob), cudaFree(p->d_ans), cudaFree(p->d_score), cudaFree(p->d_delta), cudaFree(p->d_psi);
-    cudaFree(p->d_vecs), cudaFree(p->d_ismid), cudaFree(p->d_endstate), cudaFree(p->d_sync), cudaFree(p->d_bs_score);
+    cudaFree(p->d_vecs), cudaFree(p->d_ismid), cudaFree(p->d_endstate), cudaFree(p->d_sync), cudaFree(p->d_btmap), cudaFree(p->d_bs_score);
     cudaFree(p->d_nactive);
     delete p;
 }

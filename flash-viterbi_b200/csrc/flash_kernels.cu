@@ -470,6 +470,69 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned l
     __syncthreads();
 }
 
+// The walk back of the long first pass, in parallel: window w of consecutive backpointer rows goes to CTA w (shared
+// memory, as in k_flash_backtrack_staged), which first composes its rows into ONE map — the state below the window for
+// every state above it, K independent walks at shared-memory latency — then CTA 0 chains the W maps from the end
+// state (W dependent L2 reads instead of T), and every CTA walks its own window once more from the state it was
+// handed, recording the division points (F:196-201).  46 us -> 15 us for T=256 at K=3965.
+__global__ void __launch_bounds__(1024) k_flash_backtrack_par(const VecDesc *__restrict__ vecs, const void *__restrict__ psi, int psi16,
+                                                             int K, int T, const uint8_t *__restrict__ ismid,
+                                                             const int32_t *__restrict__ endstate, int32_t *__restrict__ ans,
+                                                             int win_rows, int32_t *__restrict__ maps, unsigned long long *bar,
+                                                             unsigned long long bar_base, const float *__restrict__ final_delta, int Kp,
+                                                             float *__restrict__ score, int32_t *__restrict__ endstate_out)
+{
+    extern __shared__ uint4 swin[];
+    const VecDesc vd = vecs[0];
+    const int w = blockIdx.x, W = gridDim.x;
+    // the end state (F:188-195 / F:248) is found here too, by the CTA with the (shorter) last window, while the others compose
+    if (w == W - 1) end_body(vd, 0, final_delta, K, Kp, T, ans, score, endstate_out);
+    int32_t *starts = maps + (size_t)W * K;
+    const size_t esz = psi16 ? 2 : 4;
+    const size_t row_bytes = (size_t)K * esz;
+    int32_t *out = ans + (size_t)vd.seq * T;
+    const int jhi = vd.R - w * win_rows, jlo = max(jhi - win_rows + 1, vd.mid + 1);  // the host sizes the grid so that jhi >= jlo
+    const size_t lo = (size_t)(vd.psi_row + (jlo - vd.mid - 1)) * row_bytes;
+    const size_t hi = (size_t)(vd.psi_row + (jhi - vd.mid - 1) + 1) * row_bytes;
+    const size_t lo16 = lo & ~(size_t)15;
+    const int n16 = (int)((hi - lo16 + 15) >> 4);
+    const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(psi) + lo16);
+    for (int t0 = threadIdx.x; t0 < n16; t0 += 8 * blockDim.x) {
+        uint4 buf[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (t0 + u * blockDim.x < n16) buf[u] = __ldcg(src + t0 + u * blockDim.x);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (t0 + u * blockDim.x < n16) swin[t0 + u * blockDim.x] = buf[u];
+    }
+    __syncthreads();
+    const unsigned char *base = reinterpret_cast<const unsigned char *>(swin) + (lo - lo16);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        int state = i;
+        for (int j = jhi; j >= jlo; --j)
+            if (state >= 0) state = psi_load(base, psi16, (size_t)(j - jlo) * K + state);
+        maps[(size_t)w * K + i] = state;
+    }
+    grid_barrier(bar, bar_base + W);
+    if (w == 0 && threadIdx.x == 0) {
+        int state = __ldcg(endstate_out);  // written by CTA W-1 before the barrier
+        for (int x = 0; x < W; ++x) {
+            starts[x] = state;
+            if (state >= 0) state = __ldcg(maps + (size_t)x * K + state);
+        }
+        if (!(vd.flags & VEC_FIRST_PASS)) out[vd.mid] = state;
+    }
+    grid_barrier(bar, bar_base + 2ull * W);
+    if (threadIdx.x == 0 && (vd.flags & VEC_FIRST_PASS)) {
+        int state = __ldcg(starts + w);
+        for (int j = jhi; j >= jlo; --j) {
+            if (state >= 0) state = psi_load(base, psi16, (size_t)(j - jlo) * K + state);
+            if (ismid[j - 1]) out[j - 1] = state;
+        }
+    }
+}
+
 struct LevelArgs {
     StepArgs st;           // tables, vectors, observations, backpointer store (s, nact, din, dout are set per step)
     const double *LBd, *LPi;
@@ -902,12 +965,30 @@ int flash_run_pass(flashv_plan *p, const Pass &pass, bool time_it)
     }
     if (time_it) FV_CUDA(cudaEventRecord(ctx->ev[3], st));
 
-    // Only full-range vectors read delta here, and they run all max_steps steps of the pass.
-    k_flash_end<<<pass.nvec, 256, 0, st>>>(vecs, pass.nvec, final_delta, K, Kp, T, p->d_ans, p->d_score, p->d_endstate);
-    FV_CUDA(cudaGetLastError());
     const size_t row_bytes = (size_t)K * (p->psi16 ? 2 : 4);
     const int win_rows = (int)((200 * 1024 - 32) / row_bytes);
-    if (pass.nvec == 1 && pass.max_steps >= 16 && win_rows >= 4) {
+    const int bt_rows = pass.first_vec.R - pass.first_vec.mid;
+    const int bt_W = win_rows > 0 ? (bt_rows + win_rows - 1) / win_rows : 0;
+    const bool par_walk = pass.nvec == 1 && pass.max_steps >= 16 && win_rows >= 4 && bt_W >= 2 && bt_W <= ctx->sm_count &&
+                          bt_W < p->bt_windows && ctx->coop && p->d_btmap && !getenv("FLASHV_BACKTRACK_SERIAL");
+    if (!par_walk) {
+        // Only full-range vectors read delta here, and they run all max_steps steps of the pass.
+        k_flash_end<<<pass.nvec, 256, 0, st>>>(vecs, pass.nvec, final_delta, K, Kp, T, p->d_ans, p->d_score, p->d_endstate);
+        FV_CUDA(cudaGetLastError());
+    }
+    if (par_walk) {
+        const size_t smem = (size_t)win_rows * row_bytes + 32;
+        FV_CUDA(cudaFuncSetAttribute(k_flash_backtrack_par, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        const void *bpsi = pass_psi(p, pass);
+        int psi16 = p->psi16, wr = win_rows;
+        unsigned long long *bar = reinterpret_cast<unsigned long long *>(p->d_sync), bar_base = p->bar_count;
+        p->bar_count += 2ull * bt_W;
+        int Kp_ = Kp;
+        void *params[] = {(void *)&vecs, (void *)&bpsi, (void *)&psi16, (void *)&K, (void *)&T, (void *)&p->d_ismid, (void *)&p->d_endstate,
+                          (void *)&p->d_ans, (void *)&wr, (void *)&p->d_btmap, (void *)&bar, (void *)&bar_base, (void *)&final_delta,
+                          (void *)&Kp_, (void *)&p->d_score, (void *)&p->d_endstate};
+        FV_CUDA(cudaLaunchCooperativeKernel((const void *)k_flash_backtrack_par, dim3(bt_W), dim3(1024), params, smem, st));
+    } else if (pass.nvec == 1 && pass.max_steps >= 16 && win_rows >= 4) {
         const size_t smem = (size_t)win_rows * row_bytes + 32;
         FV_CUDA(cudaFuncSetAttribute(k_flash_backtrack_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         k_flash_backtrack_staged<<<1, 1024, smem, st>>>(vecs, pass_psi(p, pass), p->psi16, K, T, p->d_ismid, p->d_endstate, p->d_ans,

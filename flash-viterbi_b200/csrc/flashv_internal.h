@@ -142,6 +142,8 @@ struct flashv_plan {
     uint8_t *d_ismid = nullptr;   // [T] 1 where a first-pass segment boundary sits
     int *d_nactive = nullptr;     // every pass's nactive[] back to back (the persistent level kernel reads it)
     int32_t *d_endstate = nullptr;  // [max_vec]
+    int32_t *d_btmap = nullptr;     // [bt_windows][K] composed backpointer maps + [bt_windows] start states (parallel walk back)
+    int bt_windows = 0;
     unsigned int *d_sync = nullptr; // 256 zeroed bytes: the level kernel's grid-barrier counter (64-bit, monotone)
     unsigned long long bar_count = 0;  // what that counter holds once every launch issued so far has finished
     // state sharding of single-vector passes
