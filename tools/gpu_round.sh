@@ -28,5 +28,7 @@ Q="python tools/profile_target.py --beam 128 --segments 8 --iters 1"
 $Q > gpurun_out/plain_bs.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_bs_pass -c 1 -f -o gpurun_out/prof_bs $Q > gpurun_out/ncu_bs.log 2>&1
 R="python tools/profile_target.py --engine persistent --segments 8 --iters 2"
-ncu --set full --clock-control none --import-source on -k regex:k_flash_level -c 1 -f -o gpurun_out/prof_levelk $R > gpurun_out/ncu_levelk.log 2>&1
-cat gpurun_out/plain_persist.log gpurun_out/plain_bs.log
+$R > gpurun_out/plain_level.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_flash_level16 -c 1 -f -o gpurun_out/prof_level16 $R > gpurun_out/ncu_level16.log 2>&1
+FLASHV_TRACE_FILE=gpurun_out/trace.bin $P > /dev/null 2>&1 && python tools/trace_report.py gpurun_out/trace.bin > gpurun_out/phase_trace.txt 2>&1
+cat gpurun_out/plain_persist.log gpurun_out/plain_bs.log gpurun_out/plain_level.log
