@@ -447,10 +447,11 @@ def run_ours(args):
             "f16x2_issue_basis": "1 lane-instruction per update (HADD2 and HMNMX2 each cover two updates) against 148 SMs x 128 lanes x SM clock",
             "us_per_step": fp_mean * 1e3 / (T - 1),
             "tensor_memory_bytes_per_step_per_sm": int(tmem_bytes),
-            "tensor_memory_path_frac": tmem_bytes / step_s / (64 * sm_hz),
             "shared_memory_bytes_per_step_per_sm": int(smem_bytes),
-            "operand_path_basis": "table slice (2 B per update) read from tensor memory at ~64 B/clk per SM; 14 warps' half-precision delta reads from shared memory; "
-                                  "the rest of a step is the hand-over (poll, two CTA barriers) and the exact evaluation (one HBM round trip)",
+            "on_chip_bytes_per_clk_per_sm_over_the_whole_step": (tmem_bytes + smem_bytes) / step_s / sm_hz,
+            "operand_path_basis": "table slice (2 B per update) read from tensor memory, 14 warps' half-precision delta reads from shared memory; the sweep itself is "
+                                  "about 1.0 us of the step (profiles/r02_persist16_phase_trace.txt: ~110 B/clk per SM out of tensor memory), the rest is the hand-over "
+                                  "(publish -> L2 -> poll, one CTA barrier) and the exact evaluation (one HBM round trip)",
         }
     elif fp_mean > 0:
         fp32_lane_ops = (T - 1) * float(K) * K * 3
