@@ -255,7 +255,7 @@ extern "C" void flashv_model_destroy(flashv_model *m)
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     for (flashv_plan *p : m->plan_cache) flashv_plan_destroy(p);
-    cudaFree(m->hiT), cudaFree(m->hiC), cudaFree(m->LAc), cudaFree(m->LBmax), cudaFree(m->hi16), cudaFree(m->LAc16), cudaFree(m->hiS), cudaFree(m->csc_ptr), cudaFree(m->csc_k), cudaFree(m->csc_la), cudaFree(m->csr_cut), cudaFree(m->csr_i), cudaFree(m->csr_la), cudaFree(m->LAd), cudaFree(m->LBf), cudaFree(m->LBd), cudaFree(m->LPi);
+    cudaFree(m->hiT), cudaFree(m->hiC), cudaFree(m->LAc), cudaFree(m->LAcL), cudaFree(m->LBmax), cudaFree(m->hi16), cudaFree(m->LAc16), cudaFree(m->hiS), cudaFree(m->csc_ptr), cudaFree(m->csc_k), cudaFree(m->csc_la), cudaFree(m->csr_cut), cudaFree(m->csr_i), cudaFree(m->csr_la), cudaFree(m->LAd), cudaFree(m->LBf), cudaFree(m->LBd), cudaFree(m->LPi);
     cudaFree(m->scratch_f), cudaFree(m->scratch_i), cudaFree(m->scratch_x);
     delete m;
 }

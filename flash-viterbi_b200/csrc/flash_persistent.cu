@@ -160,6 +160,8 @@ struct PersistArgs {
     const float *hiC;  // CTA-tiled (float)log A of the columns [col_begin, col_begin+ncol), tile_geom.h
     int col_begin, ncol;  // destination columns this GPU owns (all of them unless the pass is state-sharded)
     const double *LAc;  // chain-major double table of models up to 4096 states (tables.cu), else null
+    const double *LAcL;  // the same for wider models: 128 chains of `clp` elements (Kp/128 rounded up to 32), else null
+    int clp;
     // the half-precision filter (k_flash_persist16): models up to 4096 states, unsharded passes
     const __half *hi16;   // (half)log A, CTA-tiled [cta][iteration of 256 states][column][256], -inf padding
     const double *LAc16;  // log A chain-major for 256 chains of 16: [(i * 256 + (k & 255)) * 16 + (k >> 8)]
@@ -371,14 +373,49 @@ __device__ __noinline__ Best scan_slow(float cm0, float cm1, float cm2, float cm
     return acc;
 }
 
+// Wider models (chains longer than 32): the chains inside the window straight from the chain-major double table
+// LAcL[(i * 128 + q) * clp + u] — coalesced 256-byte requests, several in flight — instead of scan_slow()'s
+// element-wise re-read of the tiled float table followed by a dependent load of the double.
+__device__ __noinline__ Best scan_long(float cm0, float cm1, float cm2, float cm3, int thr, float tmp, const float *sdelta,
+                                       const double *__restrict__ col, int clp, int K, int lane)
+{
+    Best acc{-FLT_MAX, 0x7fffffff};
+    const float cm[4] = {cm0, cm1, cm2, cm3};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned hit = __ballot_sync(FULL_MASK, ford(cm[c]) >= thr);
+        while (hit) {
+            const int q = 4 * (__ffs(hit) - 1) + c;
+            hit &= hit - 1;
+            const double *ch = col + (size_t)q * clp;
+#pragma unroll 4
+            for (int u = lane; u < clp; u += 32) {
+                const double la = __ldg(ch + u);
+                const int k = q + 128 * u;
+                if (k < K) {
+                    const float pre = __fadd_rn(tmp, sdelta[k]);
+                    if (ford(__fadd_rn(pre, __double2float_rn(la))) >= thr) {
+                        const float x = exact_cand(pre, la);
+                        if (x > -FLT_MAX) best_take(acc, x, k);
+                    }
+                }
+            }
+        }
+    }
+    return acc;
+}
+
 // The column's winner: exact candidates of everything inside the window, best of the warp.
 __device__ __forceinline__ Best scan_settle(const Scan &sc, const float (&cm)[4], float tmp,
                                             const float *__restrict__ round_base, int ncr, int rr, const float *sdelta,
-                                            const double *__restrict__ LAd, int K, int Kp, int i, int lane)
+                                            const double *__restrict__ LAd, const double *__restrict__ LAcL, int clp, int K, int Kp,
+                                            int i, int lane)
 {
     Best acc{-FLT_MAX, 0x7fffffff};
     if (sc.live) {
-        if (sc.overflow) {
+        if (sc.overflow && LAcL != nullptr) {
+            acc = scan_long(cm[0], cm[1], cm[2], cm[3], ford(sc.thr), tmp, sdelta, LAcL + (size_t)i * 128 * clp, clp, K, lane);
+        } else if (sc.overflow) {
             acc = scan_slow(cm[0], cm[1], cm[2], cm[3], ford(sc.thr), tmp, round_base, ncr, rr, sdelta, LAd, K, Kp, i, lane);
         } else {
             const int k0 = sc.q0 + 128 * lane, k1 = sc.q1 + 128 * lane;  // element `lane` of either chain
@@ -664,7 +701,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
             scan_fetch(s0, cm0, a.LAc, i0, true, lane);
             scan_fetch(s1, cm1, a.LAc, i1, have1, lane);
             if (tracing) tr[3] = clock64();
-            const Best r0 = scan_settle(s0, cm0, tmp0, round_base, ncr, rr0, sdelta, a.LAd, a.K, a.Kp, i0, lane);
+            const Best r0 = scan_settle(s0, cm0, tmp0, round_base, ncr, rr0, sdelta, a.LAd, a.LAcL, a.clp, a.K, a.Kp, i0, lane);
             if (lane == 0) {
                 if (PEERS) {
                     if (keep)
@@ -679,7 +716,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_flash_persist(const PersistArgs
                 }
             }
             if (have1) {
-                const Best r1 = scan_settle(s1, cm1, tmp1, round_base, ncr, rr1, sdelta, a.LAd, a.K, a.Kp, i1, lane);
+                const Best r1 = scan_settle(s1, cm1, tmp1, round_base, ncr, rr1, sdelta, a.LAd, a.LAcL, a.clp, a.K, a.Kp, i1, lane);
                 if (lane == 0) {
                     if (PEERS) {
                         if (keep)
@@ -1107,7 +1144,7 @@ int persistent_pass(flashv_plan *p, const Pass &pass)
     flashv_model *m = p->model;
     const VecDesc &vd = pass.first_vec;  // the pass has exactly one vector (batch == 1)
     PersistArgs a;
-    a.LAd = m->LAd, a.LAc = m->LAc, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+    a.LAd = m->LAd, a.LAc = m->LAc, a.LAcL = m->LAcL, a.clp = m->clp, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.ob = p->d_ob;
     a.L = vd.L, a.nsteps = vd.R - vd.L, a.mid = vd.mid, a.psi_row = vd.psi_row;
     a.d_init = p->d_delta, a.d_final = p->d_delta + (size_t)p->max_vec * m->Kp;
@@ -1228,7 +1265,7 @@ int persistent_single_step(flashv_model *m, const float *d_in_dev, int o, float 
     PersistArgs a;
     a.hiC = m->hiC, a.col_begin = 0, a.ncol = m->K, a.npeer = 1;
     a.hi16 = m->hi16, a.LAc16 = m->LAc16, a.Kp16 = m->Kp16, a.LBmax = m->LBmax, a.lamax = m->lamax;
-    a.LAd = m->LAd, a.LAc = m->LAc, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+    a.LAd = m->LAd, a.LAc = m->LAc, a.LAcL = m->LAcL, a.clp = m->clp, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
     a.ob = dob, a.L = 0, a.nsteps = 1, a.mid = 0, a.psi_row = 0;
     static unsigned hook_epoch = 0;
     a.epoch = (++hook_epoch & 0xffffu) ? (hook_epoch & 0xffffu) : (++hook_epoch & 0xffffu);

@@ -95,6 +95,8 @@ struct flashv_model {
     float *hiT = nullptr;     // [K][Kp]  (float)log A, destination-major: hiT[i][k] = log A[k][i]; pad = -inf
     float *hiC = nullptr;     // K*Kp     the same, CTA-tiled for the persistent engine (tile_geom.h)
     double *LAc = nullptr;    // K*4096   log A chain-major for the persistent engine's window scan (K <= 4096 only)
+    double *LAcL = nullptr;   // K*128*clp the same for wider models: chains of clp = Kp/128 (rounded up to 32) elements
+    int clp = 0;
     __half *hi16 = nullptr;   // K*Kp16   (half)log A, CTA-tiled for the half-precision filter (K <= 4096 only)
     double *LAc16 = nullptr;  // K*4096   log A chain-major for that filter: 256 chains of 16
     int Kp16 = 0;             // K rounded up to 256

@@ -102,6 +102,16 @@ __global__ void k_build_tiled16(const double *__restrict__ LAd, __half *__restri
     }
 }
 
+// LAcL: the chain-major double table of models wider than 4096 states (flash_persistent.cu: scan_long): 128 chains
+// of clp = Kp/128 rounded up to 32 elements per destination column, -inf padding.
+__global__ void k_build_long_chains(const double *__restrict__ LAd, double *__restrict__ LAcL, int K, int clp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // coalesced reads along i, scattered 8-byte writes
+    const int k = blockIdx.y;                             // 0 .. 128 * clp - 1
+    if (i >= K) return;
+    LAcL[((size_t)i * 128 + (k & 127)) * clp + (k >> 7)] = k < K ? LAd[(size_t)k * K + i] : -INFINITY;
+}
+
 void build_tiled_slice(const double *LAd, float *hiC, int K, int Kp, int col_begin, int ncol, int G, cudaStream_t st)
 {
     k_build_tiled<<<dim3((ncol + 255) / 256, Kp), 256, 0, st>>>(LAd, hiC, K, Kp, col_begin, ncol, G);
@@ -273,6 +283,21 @@ int tables_layouts(flashv_model *m)
     m->tile_G = ctx->sm_count < K ? ctx->sm_count : K;
     build_tiled_slice(m->LAd, m->hiC, K, Kp, 0, K, m->tile_G, ctx->stream);
     FV_CUDA(cudaGetLastError());
+    if (Kp > 4096) {
+        // wider models: long chains, if the table (as large as LAd) is affordable; FLASHV_LACL_MAX_GB moves the limit
+        const int clp = ((Kp >> 7) + 31) / 32 * 32;
+        const size_t bytes = (size_t)K * 128 * clp * sizeof(double);
+        const char *e = getenv("FLASHV_LACL_MAX_GB");
+        const size_t max_gb = e ? (size_t)atol(e) : 32;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (bytes <= max_gb << 30 && bytes + ((size_t)8 << 30) <= free_b && 128 * clp <= 65535) {
+            FV_CUDA(cudaMalloc(&m->LAcL, bytes));
+            m->bytes += bytes, m->clp = clp;
+            k_build_long_chains<<<dim3((K + 255) / 256, 128 * clp), 256, 0, ctx->stream>>>(m->LAd, m->LAcL, K, clp);
+            FV_CUDA(cudaGetLastError());
+        }
+    }
     if (Kp <= 4096) {
         FV_CUDA(cudaMalloc(&m->LAc, (size_t)K * 4096 * sizeof(double)));
         m->bytes += (size_t)K * 4096 * sizeof(double);
