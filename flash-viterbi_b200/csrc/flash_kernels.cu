@@ -645,11 +645,7 @@ __global__ void __launch_bounds__(L16_THREADS, 1) k_flash_level16(const LevelArg
     const bool have0 = rr0 < ncols, have1 = rr1 < ncols;
     const int rs0 = have0 ? rr0 : 0, rs1 = have1 ? rr1 : rs0;  // a duplicate row stands in for a missing one
     const int i0 = c0 + rs0, i1 = c0 + rs1;
-    if (have0)
-        for (int it = 0; it < n_it; ++it) {
-            tmem_st4_raw(tbase + 8u * (uint32_t)it, __ldg(reinterpret_cast<const uint4 *>(slab + ((size_t)it * ncols + rs0) * 256) + lane));
-            tmem_st4_raw(tbase + 8u * (uint32_t)it + 4u, __ldg(reinterpret_cast<const uint4 *>(slab + ((size_t)it * ncols + rs1) * 256) + lane));
-        }
+    if (have0) tmem_fill16(tbase, slab, ncols, rs0, rs1, n_it, lane);
     tmem_wait_st();
     tmem_fence_before();
 

@@ -69,6 +69,30 @@ __device__ __forceinline__ void tmem_st4_raw(uint32_t taddr, const uint4 &v)
 }
 
 
+// Park the first n_it iterations (256 source states each) of a warp's two columns of the tiled half table in its
+// tensor-memory slot: columns 8 it .. 8 it + 3 hold the first column's eight halves per lane, 8 it + 4 .. + 7 the
+// second's.  Eight 16-byte loads are requested before any of them is stored: the tcgen05.st is volatile, so a load
+// written next to its store would wait for memory alone, once per iteration and column (32 round trips per launch).
+__device__ __forceinline__ void tmem_fill16(uint32_t tbase, const __half *__restrict__ slab, int ncols, int rs0, int rs1, int n_it,
+                                            int lane)
+{
+    for (int it0 = 0; it0 < n_it; it0 += 4) {
+        uint4 va[4], vb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int it = min(it0 + e, n_it - 1);
+            va[e] = __ldg(reinterpret_cast<const uint4 *>(slab + ((size_t)it * ncols + rs0) * 256) + lane);
+            vb[e] = __ldg(reinterpret_cast<const uint4 *>(slab + ((size_t)it * ncols + rs1) * 256) + lane);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (it0 + e < n_it) {
+                tmem_st4_raw(tbase + 8u * (uint32_t)(it0 + e), va[e]);
+                tmem_st4_raw(tbase + 8u * (uint32_t)(it0 + e) + 4u, vb[e]);
+            }
+    }
+}
+
 template <int P>
 struct Scan16T {
     double la[P];  // pair p: lanes 0-15 hold the elements of chain qa[p], lanes 16-31 those of qb[p]
