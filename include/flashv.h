@@ -41,7 +41,10 @@ typedef struct flashv_plan flashv_plan;   /* decode schedule + workspace for one
  * K <= 56,320 (one delta vector in shared memory); a forced engine that does not fit is FLASHV_ERR_ARG. */
 #define FLASHV_ENGINE_AUTO 0
 #define FLASHV_ENGINE_STEP 1       /* one kernel launch per trellis step */
-#define FLASHV_ENGINE_PERSISTENT 2 /* one cooperative launch per pass, TMA-fed; steps hand over through tagged delta words, no grid barrier */
+#define FLASHV_ENGINE_PERSISTENT 2 /* one cooperative launch per pass; steps hand over through tagged delta words, no grid barrier.  Models up
+                                      to 4096 states: the table slice of every SM stays in tensor memory and the sweep is a half-precision
+                                      filter (every candidate inside its window is then evaluated with the reference's arithmetic: results
+                                      are bit-identical); wider models: float sweep, TMA-fed ring, first 2048 states in tensor memory */
 #define FLASHV_ENGINE_SPARSE 3     /* opt-in: the pass walks the in-edge lists (entries with A[k][i] == 0 can never win,
                                       F:171), resident in shared memory; same results, not the dense roofline's bytes */
 
