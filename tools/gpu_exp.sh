@@ -1,18 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-FLASHV_PREP_TRACE=1 python - <<'PY'
-import sys, time
-sys.path.insert(0, "flash-viterbi_b200/host")
-import numpy as np
-from __graft_entry__ import load_pkg
-import gen_hmm
-fv = load_pkg()
-A, B, Pi = gen_hmm.make_hmm(3965, 50, 0.112, 1)
-ctx = fv.Context(0)
-for it in range(3):
-    t0 = time.perf_counter()
-    m = fv.Model(ctx, A, B, Pi)
-    t1 = time.perf_counter()
-    print(f"== model {it}: wall {1e3*(t1-t0):.1f} ms, prep_ms {m.prep_ms:.1f}", flush=True)
-    m.close()
-PY
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 -p no:cacheprovider -k "goldens or golden_vectors or bench_instance_flash or random_models or level_kernel or wide_model or batch_equals or headline_flash_vs" > gpurun_out/pytest_res.log 2>&1
+tail -2 gpurun_out/pytest_res.log
+for N in 1 8 64 127; do python tools/profile_target.py --engine persistent --segments $N --iters 4; done
