@@ -286,6 +286,33 @@ def test_half_precision_filter_bound():
     assert widest >= 2 and slow >= 1  # multi-chain windows and the distrust regime both occurred
 
 
+def test_half_filter_normaliser_is_a_bound():
+    """k_flash_persist16 normalises the arriving vector by c = fl32(fl64(fl32(max tmp + max delta_prev) + max log A)),
+    derived one step ahead; the filter's error analysis needs c >= every entry of the vector (no cancellation).
+    All roundings in the reference's chain are monotone, so the bound must hold exactly, in float arithmetic."""
+    rng = np.random.RandomState(41)
+    for trial in range(200):
+        K = 150
+        A = rng.uniform(0.01, 1, (K, K)) * (rng.uniform(0, 1, (K, K)) < rng.choice([0.1, 0.5, 1.0]))
+        A = (A / np.maximum(A.sum(axis=1, keepdims=True), 1e-9)).astype(np.float32)
+        with np.errstate(divide="ignore"):
+            la = np.log(A.astype(np.float64))
+        tmp = np.float32(-rng.uniform(0, 6, K))
+        d = (np.float32(-rng.uniform(0, 8, K)) * np.float32(rng.choice([1, 30, 900]))).astype(np.float32)
+        if trial % 4 == 0:
+            d[rng.randint(0, K, K // 3)] = np.float32(-3.4028234663852886e38)
+        pre = (tmp[None, :] + d[:, None]).astype(np.float32)  # [k][i]
+        with np.errstate(over="ignore", invalid="ignore"):
+            cand = (pre.astype(np.float64) + la).astype(np.float32)
+        nxt = cand.max(axis=0)
+        bound = np.float32(np.float64(np.float32(tmp.max() + d.max())) + la.max())
+        assert (nxt <= bound).all(), trial
+        # ... and it is tight enough to be useful: within the spread of one step's terms
+        live = nxt > np.float32(-3.0e38)
+        if live.any() and np.isfinite(bound):
+            assert bound - nxt[live].max() < 40.0
+
+
 def test_header_declares_only_exported_symbols(fv):
     text = (ROOT / "include" / "flashv.h").read_text()
     declared = sorted(set(re.findall(r"\b(flashv_[a-z_A-Z0-9]+)\s*\(", text)))
