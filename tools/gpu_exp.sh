@@ -1,6 +1,6 @@
 #!/bin/bash
+# scratch script for the experiment at hand (one gpurun call): parity subset, then timings of the default decodes
 mkdir -p gpurun_out
-P="python tools/profile_target.py --engine persistent --segments 63 --iters 2 --K 16384 --T 64"
-$P > gpurun_out/plain_k16384.log 2>&1 && cat gpurun_out/plain_k16384.log &&
-ncu --set full --clock-control none --import-source on -k regex:k_flash_persist -s 1 -c 1 -f -o gpurun_out/prof_persist_k16384 $P > gpurun_out/ncu_k16384.log 2>&1
-tail -2 gpurun_out/ncu_k16384.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 -p no:cacheprovider -k "goldens or golden_vectors or bench_instance_flash or random_models or half_filter or trellis_step" > gpurun_out/pytest_res.log 2>&1
+tail -2 gpurun_out/pytest_res.log
+for N in 1 8 64 127; do python tools/profile_target.py --engine persistent --segments $N --iters 4; done
