@@ -820,12 +820,45 @@ static int launch_level16(flashv_plan *p, const Pass &pass, LevelArgs &la, bool 
     return FLASHV_OK;
 }
 
+// A level whose tasks are all ONE step long (the bottom of every tree): that step is the task's last one, so each
+// task needs one column (last_column_body) and nothing from the other tasks — start vector, column, end state and
+// Ans[mid] in one ordinary launch, one CTA per task, instead of four launches.
+__global__ void __launch_bounds__(LC_WARPS * 32) k_flash_level_one_step(const LevelArgs la)
+{
+    const int v = blockIdx.x;
+    const VecDesc vd = la.st.vecs[v];
+    init_vector(vd, v, la.st.ob, la.ans, la.st.T, la.st.LAd, la.LBd, la.LPi, la.st.K, la.st.Kp, la.d0, threadIdx.x, LC_WARPS * 32);
+    __threadfence_block();
+    __syncthreads();  // the column sweep reads the vector through L2 (ld.global.cg)
+    last_column_body(la.st, 1, la.d0, v, la.ans);
+    end_body(vd, v, la.d0, la.st.K, la.st.Kp, la.st.T, la.ans, la.score, la.endstate);
+    if (threadIdx.x == 0) backtrack_vector(vd, la.endstate[v], la.st.psi, la.st.psi16, la.st.K, la.st.T, la.ismid, la.ans);
+}
+
 // Returns with *done = true when the whole pass (start vectors .. Ans[mid]) ran in one launch.
 static int level_pass(flashv_plan *p, const Pass &pass, bool *done)
 {
     flashv_model *m = p->model;
     *done = false;
     if (!m->ctx->coop || !p->d_nactive || getenv("FLASHV_LEVEL_STEPS")) return FLASHV_OK;
+    if (pass.max_steps == 1 && !pass.full_range && pass.nvec <= 65535) {
+        LevelArgs la;
+        StepArgs &a = la.st;
+        a.hiT = m->hiT, a.LAd = m->LAd, a.LBf = m->LBf, a.K = m->K, a.Kp = m->Kp;
+        a.vecs = p->d_vecs + pass.vec_offset, a.nact = pass.nvec, a.s = 1, a.din = nullptr, a.dout = nullptr;
+        a.ob = p->d_ob, a.T = p->T, a.psi = p->d_psi, a.psi16 = p->psi16;
+        la.LBd = m->LBd, la.LPi = m->LPi;
+        la.nvec = pass.nvec, la.max_steps = 1, la.full_range = 0;
+        la.nactive = nullptr;
+        la.d0 = p->d_delta, la.d1 = nullptr;
+        la.ans = p->d_ans, la.score = p->d_score, la.endstate = p->d_endstate, la.ismid = p->d_ismid;
+        la.bar = nullptr, la.bar_base = 0;
+        k_flash_level_one_step<<<pass.nvec, LC_WARPS * 32, 0, m->ctx->stream>>>(la);
+        FV_CUDA(cudaGetLastError());
+        ++p->launches;
+        *done = true;
+        return FLASHV_OK;
+    }
     // Measured (K=3965, T=256, same box): one launch per level against one per step — N=1 9.65 / 10.12 ms, N=8
     // 6.29 / 6.53 ms, N=64 2.77 / 2.75 ms, N=127 2.22 / 2.16 ms.  A level of one or two steps has nothing to
     // amortise the extra grid barriers over, so short levels keep the per-step launches.
