@@ -1,12 +1,19 @@
 // flash_persistent.cu — engine PERSISTENT: a whole single-vector FLASH pass (the N-way first pass
 // of nvviterNdivide, F:126-202, or a full-length task of nvviter, F:204-262) in ONE cooperative
-// launch, one CTA per SM.
+// launch, one CTA per SM.  Two kernels:
 //
+//   k_flash_persist16 (models up to 4096 states, unsharded — the headline pass; second half of this file)
+//     the CTA's whole slice of (half)log A lives in tensor memory for the launch; the sweep is a half-precision
+//     filter (HADD2 + HMNMX2 per two updates) with a rigorous window, and every chain inside the window is
+//     evaluated exactly from a chain-major double table.  See the comment above the kernel and DESIGN.md §4.
+//
+//   k_flash_persist<TM, PIN, PEERS> (wider models, state-sharded passes, FLASHV_F16=0)
 //   * Each CTA owns a contiguous range of destination columns (K/gridDim of them) and re-reads their
-//     log-A entries every step — from L2 when the table fits (62.9 MB at K=3965 against 126 MB of
-//     L2; ncu: 97 % L2 hit rate, 0.25 % DRAM).  The table is stored CTA-tiled (hiC, tile_geom.h):
-//     per CTA, per chunk of TILE_CH source states, the chunk of every owned column back to back,
-//     so one step of one CTA is one linear stream and every ring stage is one contiguous bulk copy.
+//     float log-A entries every step.  The table is stored CTA-tiled (hiC, tile_geom.h): per CTA, per chunk of
+//     TILE_CH source states, the chunk of every owned column back to back, so one step of one CTA is one linear
+//     stream and every ring stage is one contiguous bulk copy.  Wide models stream it from HBM at the roofline
+//     (K=16384: 6.38 TB/s); single-round CTAs keep the first 2048 states of every column in tensor memory (TM)
+//     and, when the rest fits shared memory whole, load it once (PIN).
 //   * Warp NCW is the producer: one lane streams the slab through an NSTAGE-deep shared-memory ring
 //     with bulk TMA copies (cp.async.bulk ... mbarrier::complete_tx), running ahead across step
 //     boundaries since the table does not change — the ring refills while the CTAs hand over.
@@ -14,12 +21,11 @@
 //     columns of the round (rows 2w, 2w+1 of the stage), lane l owns k = 4*(l+32u)+c and keeps four
 //     running maxima per column of the float estimate (FADD, FADD, FMNMX per update); a stage is
 //     released after NCW arrivals, so the ring is a true FIFO and no warp ever holds a stage longer
-//     than one pass over its two rows.  The exact (value, first index) comes from the double table
-//     for the few candidates inside the window (trellis_common.cuh): the winning chain is re-read
-//     from the tiled table (L2), the double loads of both columns are issued before either is
-//     consumed.
+//     than one pass over its two rows.  The exact (value, first index) comes from a chain-major double
+//     table for the chains inside the window (scan_fetch / scan_settle / scan_long below).
 //   * Steps hand over through the delta vector itself ({value, step} words polled from L2, see
-//     delta_wait_load): no grid barrier, no atomics.
+//     delta_wait_load): no grid barrier, no atomics.  PEERS: the words (and the backpointer rows) go to
+//     every GPU of a state-sharded pass with in-kernel peer stores.
 //   F: = /root/reference/src/FLASH_Viterbi_multithread.c
 #include <stdio.h>
 #include <stdlib.h>
